@@ -1,0 +1,496 @@
+"""CPU oracle for the EO_Diffusion reverse-sampling hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, as plain functions over a state dict, the algorithm of the
+reference's sampling path.  It is the checker that the CUDA path
+is compared against; it is never the thing measured or shipped.  Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may
+import it.  The product package (`eo_diffusion_b200/`) must not import it.
+
+Why torch and not numpy/C: the path is floating point, and its arithmetic lives in
+PyTorch's ATen kernels (conv2d, group_norm, softmax, einsum), which are a third-party
+dependency of the reference (pinned there at pytorch 1.13.0, `eo_diffusion.yml:114`; we
+run 2.11.0).  The restatement calls the same ATen ops in the same order, so on CPU it
+reproduces the reference bit-for-bit (checked by `oracle/make_golden.py` and by
+`tests/test_oracle.py` whenever `/root/reference` is present).
+
+Pinning status: the reference has no tests, golden vectors or known-answer fixtures for
+this path.  The oracle is pinned instead against outputs of the live
+reference imported in the build container (`oracle/make_golden.py` -> `tests/golden/`),
+plus the three constants the reference does publish: the parameter count 88.220934 M
+(`EO_Diffusion.ipynb:151`), the state-dict key names (`configs/errors.txt`) and the
+schedule end points recorded in SURVEY.md section 8c.
+
+All citations are `path:line` under the reference repository root.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+# --------------------------------------------------------------------------------------
+# UNet topology (backbones/unet_openai.py:553-744)
+# --------------------------------------------------------------------------------------
+
+DEFAULT_CFG = dict(
+    image_size=64, in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
+    attention_resolutions=(4, 8), time_emb_factor=4, dropout=0, channel_mult=(1, 2, 3, 4),
+    conv_resample=True, dims=2, num_classes=None, use_checkpoint=False, use_fp16=False,
+    num_heads=8, num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=False,
+    resblock_updown=False, use_new_attention_order=False,
+)
+
+
+def full_cfg(**kw) -> dict:
+    cfg = dict(DEFAULT_CFG)
+    cfg.update(kw)
+    return cfg
+
+
+def enumerate_blocks(cfg: dict) -> Dict[str, list]:
+    """Walk the constructor loops of UNetModel (unet_openai.py:607-737) and return, per
+    stage, the list of sub-layers as tuples:
+      ("conv_in", cin, cout) | ("res", cin, cout) | ("attn", ch, heads) |
+      ("down", ch) | ("up", ch)
+    Only the options the hot path exercises are restated (dims=2, conv_resample=True,
+    resblock_updown=False, use_scale_shift_norm=False)."""
+    assert cfg["dims"] == 2 and cfg["conv_resample"] and not cfg["resblock_updown"]
+    assert not cfg["use_scale_shift_norm"]
+    mc = cfg["model_channels"]
+    mult = list(cfg["channel_mult"])
+    nrb = cfg["num_res_blocks"]
+    heads = cfg["num_heads"]
+    heads_up = heads if cfg["num_heads_upsample"] == -1 else cfg["num_heads_upsample"]
+    nhc = cfg["num_head_channels"]
+    attn_res = set(cfg["attention_resolutions"])
+
+    def nheads(ch, h):
+        return h if nhc == -1 else ch // nhc
+
+    ch = int(mult[0] * mc)
+    inputs = [[("conv_in", cfg["in_channels"], ch)]]
+    chans = [ch]
+    ds = 1
+    for level, m in enumerate(mult):
+        for _ in range(nrb):
+            layers = [("res", ch, int(m * mc))]
+            ch = int(m * mc)
+            if ds in attn_res:
+                layers.append(("attn", ch, nheads(ch, heads)))
+            inputs.append(layers)
+            chans.append(ch)
+        if level != len(mult) - 1:
+            inputs.append([("down", ch)])
+            chans.append(ch)
+            ds *= 2
+    middle = [("res", ch, ch), ("attn", ch, nheads(ch, heads)), ("res", ch, ch)]
+    outputs = []
+    for level, m in list(enumerate(mult))[::-1]:
+        for i in range(nrb + 1):
+            ich = chans.pop()
+            layers = [("res", ch + ich, int(mc * m))]
+            ch = int(mc * m)
+            if ds in attn_res:
+                layers.append(("attn", ch, nheads(ch, heads_up)))
+            if level and i == nrb:
+                layers.append(("up", ch))
+                ds //= 2
+            outputs.append(layers)
+    return {"input": inputs, "middle": middle, "output": outputs, "final_ch": ch}
+
+
+# --------------------------------------------------------------------------------------
+# primitives
+# --------------------------------------------------------------------------------------
+
+def timestep_embedding(timesteps: Tensor, dim: int, max_period: int = 10000) -> Tensor:
+    """unet_openai.py:81-99 (== nn.py:103-121)."""
+    half = dim // 2
+    freqs = torch.exp(
+        -math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half
+    ).to(device=timesteps.device)
+    args = timesteps[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+def group_norm32(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
+    """GroupNorm32 (unet_openai.py:11-13): 32 groups, eps 1e-5, evaluated in fp32."""
+    return F.group_norm(x.float(), 32, w, b, 1e-5).type(x.dtype)
+
+
+def res_block(sd: dict, p: str, x: Tensor, emb: Tensor) -> Tensor:
+    """ResBlock._forward, non-updown, no scale-shift (unet_openai.py:365-385)."""
+    h = group_norm32(x, sd[p + "in_layers.0.weight"], sd[p + "in_layers.0.bias"])
+    h = F.silu(h)
+    h = F.conv2d(h, sd[p + "in_layers.2.weight"], sd[p + "in_layers.2.bias"], padding=1)
+    e = F.linear(F.silu(emb), sd[p + "emb_layers.1.weight"], sd[p + "emb_layers.1.bias"])
+    h = h + e.type(h.dtype)[..., None, None]
+    h = group_norm32(h, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"])
+    h = F.silu(h)
+    # Dropout(p=dropout) at out_layers.2: identity at inference / p=0
+    h = F.conv2d(h, sd[p + "out_layers.3.weight"], sd[p + "out_layers.3.bias"], padding=1)
+    if (p + "skip_connection.weight") in sd:
+        x = F.conv2d(x, sd[p + "skip_connection.weight"], sd[p + "skip_connection.bias"])
+    return x + h
+
+
+def qkv_attention(qkv: Tensor, n_heads: int, new_order: bool) -> Tensor:
+    """QKVAttentionLegacy.forward (unet_openai.py:465-481) / QKVAttention.forward
+    (:497-515)."""
+    bs, width, length = qkv.shape
+    assert width % (3 * n_heads) == 0
+    ch = width // (3 * n_heads)
+    scale = 1 / math.sqrt(math.sqrt(ch))
+    if not new_order:
+        q, k, v = qkv.reshape(bs * n_heads, ch * 3, length).split(ch, dim=1)
+        w = torch.einsum("bct,bcs->bts", q * scale, k * scale)
+    else:
+        q, k, v = qkv.chunk(3, dim=1)
+        w = torch.einsum(
+            "bct,bcs->bts",
+            (q * scale).view(bs * n_heads, ch, length),
+            (k * scale).view(bs * n_heads, ch, length),
+        )
+        v = v.reshape(bs * n_heads, ch, length)
+    w = torch.softmax(w.float(), dim=-1).type(w.dtype)
+    a = torch.einsum("bts,bcs->bct", w, v)
+    return a.reshape(bs, -1, length)
+
+
+def attention_block(sd: dict, p: str, x: Tensor, n_heads: int, new_order: bool) -> Tensor:
+    """AttentionBlock._forward (unet_openai.py:427-433)."""
+    b, c, *spatial = x.shape
+    x = x.reshape(b, c, -1)
+    h = group_norm32(x, sd[p + "norm.weight"], sd[p + "norm.bias"])
+    qkv = F.conv1d(h, sd[p + "qkv.weight"], sd[p + "qkv.bias"])
+    h = qkv_attention(qkv, n_heads, new_order)
+    h = F.conv1d(h, sd[p + "proj_out.weight"], sd[p + "proj_out.bias"])
+    return (x + h).reshape(b, c, *spatial)
+
+
+def downsample(sd: dict, p: str, x: Tensor) -> Tensor:
+    """Downsample.forward with conv_resample (unet_openai.py:257-271)."""
+    return F.conv2d(x, sd[p + "op.weight"], sd[p + "op.bias"], stride=2, padding=1)
+
+
+def upsample(sd: dict, p: str, x: Tensor) -> Tensor:
+    """Upsample.forward (unet_openai.py:229-242); the 3x3 -> 7x7 pad quirk (:237-239) is
+    unreachable at supported sizes and is asserted away."""
+    assert not (x.shape[-1] == x.shape[-2] == 3)
+    out = F.interpolate(x, scale_factor=2, mode="nearest")
+    return F.conv2d(out, sd[p + "conv.weight"], sd[p + "conv.bias"], padding=1)
+
+
+def _run_layers(sd, prefix, layers, h, emb, new_order):
+    for j, layer in enumerate(layers):
+        p = f"{prefix}{j}."
+        kind = layer[0]
+        if kind == "conv_in":
+            h = F.conv2d(h, sd[p + "weight"], sd[p + "bias"], padding=1)
+        elif kind == "res":
+            h = res_block(sd, p, h, emb)
+        elif kind == "attn":
+            h = attention_block(sd, p, h, layer[2], new_order)
+        elif kind == "down":
+            h = downsample(sd, p, h)
+        elif kind == "up":
+            h = upsample(sd, p, h)
+        else:  # pragma: no cover
+            raise ValueError(kind)
+    return h
+
+
+@torch.no_grad()
+def unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, timesteps: Tensor,
+                 cond: Optional[Tensor] = None, y: Optional[Tensor] = None,
+                 taps: Optional[dict] = None) -> Tensor:
+    """UNetModel.forward (unet_openai.py:746-780).  `sd` uses the UNet's own key names
+    (no `model.` prefix).  `taps`, if given, collects intermediate activations."""
+    if cond is not None:
+        x = torch.cat([x, cond.to(x.device)], 1)
+    assert (y is not None) == (cfg["num_classes"] is not None), \
+        "must specify y if and only if the model is class-conditional"
+    blocks = enumerate_blocks(cfg)
+    new_order = cfg["use_new_attention_order"]
+    emb = timestep_embedding(timesteps, cfg["model_channels"])
+    emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
+    emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
+    if cfg["num_classes"] is not None:
+        assert y.shape == (x.shape[0],)
+        emb = emb + F.embedding(y, sd["label_emb.weight"])
+    hs = []
+    h = x.float()
+    for i, layers in enumerate(blocks["input"]):
+        h = _run_layers(sd, f"input_blocks.{i}.", layers, h, emb, new_order)
+        hs.append(h)
+        if taps is not None:
+            taps[f"input_blocks.{i}"] = h
+    h = _run_layers(sd, "middle_block.", blocks["middle"], h, emb, new_order)
+    if taps is not None:
+        taps["middle_block"] = h
+    for i, layers in enumerate(blocks["output"]):
+        h = torch.cat([h, hs.pop()], dim=1)
+        h = _run_layers(sd, f"output_blocks.{i}.", layers, h, emb, new_order)
+        if taps is not None:
+            taps[f"output_blocks.{i}"] = h
+    h = h.type(x.dtype)
+    h = F.silu(group_norm32(h, sd["out.0.weight"], sd["out.0.bias"]))
+    return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
+
+
+# --------------------------------------------------------------------------------------
+# DDPM schedule and steps (diffusion/model.py)
+# --------------------------------------------------------------------------------------
+
+def cosine_schedule(timesteps: int, epsilon: float = 0.008) -> Dict[str, Tensor]:
+    """EODiffusion.__init__ buffers + _cosine_variance_schedule (model.py:22-32, 87-92).
+    Computed with the reference's own fp32 torch op sequence on the CPU."""
+    steps = torch.linspace(0, timesteps, steps=timesteps + 1, dtype=torch.float32)
+    f_t = torch.cos(((steps / timesteps + epsilon) / (1.0 + epsilon)) * math.pi * 0.5) ** 2
+    betas = torch.clip(1.0 - f_t[1:] / f_t[:timesteps], 0.0, 0.999)
+    alphas = 1. - betas
+    alphas_cumprod = torch.cumprod(alphas, dim=-1)
+    return {
+        "betas": betas,
+        "alphas": alphas,
+        "alphas_cumprod": alphas_cumprod,
+        "sqrt_alphas_cumprod": torch.sqrt(alphas_cumprod),
+        "sqrt_one_minus_alphas_cumprod": torch.sqrt(1. - alphas_cumprod),
+    }
+
+
+def _g(table: Tensor, t: Tensor, n: int) -> Tensor:
+    return table.gather(-1, t).reshape(n, 1, 1, 1)
+
+
+def forward_diffusion(s: dict, x_0: Tensor, t: Tensor, noise: Tensor) -> Tensor:
+    """EODiffusion._forward_diffusion (model.py:94-98)."""
+    assert x_0.shape == noise.shape
+    n = x_0.shape[0]
+    return _g(s["sqrt_alphas_cumprod"], t, n) * x_0 + \
+        _g(s["sqrt_one_minus_alphas_cumprod"], t, n) * noise
+
+
+def sum_mix(s: dict, x_t: Tensor, gt: Tensor, mask: Tensor, t: Tensor, noise: Tensor) -> Tensor:
+    """The RePaint-style 'sum' conditioning mix (model.py:58-60)."""
+    gt_noised = forward_diffusion(s, gt, t, noise)
+    return mask * gt_noised + (1 - mask) * x_t
+
+
+def reverse_step_clip(s: dict, x_t: Tensor, t: Tensor, noise: Tensor, pred: Tensor) -> Tensor:
+    """EODiffusion._reverse_diffusion_with_clip after the UNet call (model.py:133-150)."""
+    n = x_t.shape[0]
+    alpha_t = _g(s["alphas"], t, n)
+    alpha_t_cumprod = _g(s["alphas_cumprod"], t, n)
+    beta_t = _g(s["betas"], t, n)
+    x_0_pred = torch.sqrt(1. / alpha_t_cumprod) * x_t - torch.sqrt(1. / alpha_t_cumprod - 1.) * pred
+    x_0_pred.clamp_(-1., 1.)
+    if t.min() > 0:
+        acp_prev = _g(s["alphas_cumprod"], t - 1, n)
+        mean = (beta_t * torch.sqrt(acp_prev) / (1. - alpha_t_cumprod)) * x_0_pred + \
+            ((1. - acp_prev) * torch.sqrt(alpha_t) / (1. - alpha_t_cumprod)) * x_t
+        std = torch.sqrt(beta_t * (1. - acp_prev) / (1. - alpha_t_cumprod))
+    else:
+        mean = (beta_t / (1. - alpha_t_cumprod)) * x_0_pred
+        std = 0.0
+    return mean + std * noise
+
+
+def reverse_step_noclip(s: dict, x_t: Tensor, t: Tensor, noise: Tensor, pred: Tensor) -> Tensor:
+    """EODiffusion._reverse_diffusion after the UNet call (model.py:110-122)."""
+    n = x_t.shape[0]
+    alpha_t = _g(s["alphas"], t, n)
+    alpha_t_cumprod = _g(s["alphas_cumprod"], t, n)
+    beta_t = _g(s["betas"], t, n)
+    somac = _g(s["sqrt_one_minus_alphas_cumprod"], t, n)
+    mean = (1. / torch.sqrt(alpha_t)) * (x_t - ((1.0 - alpha_t) / somac) * pred)
+    if t.min() > 0:
+        acp_prev = _g(s["alphas_cumprod"], t - 1, n)
+        std = torch.sqrt(beta_t * (1. - acp_prev) / (1. - alpha_t_cumprod))
+    else:
+        std = 0.0
+    return mean + std * noise
+
+
+@torch.no_grad()
+def ddpm_sample(sd: dict, cfg: dict, s: dict, x_T: Tensor, noise_tape: Sequence[Tensor],
+                cond: Optional[Tensor] = None, cond_type: Optional[str] = None,
+                clipped: bool = True, y: Optional[Tensor] = None,
+                record: Optional[list] = None, eps_fn=None) -> Tensor:
+    """EODiffusion.sampling (model.py:46-75) with the RNG replaced by a pre-drawn tape:
+    `x_T` is the initial draw (:48) and `noise_tape[k]` the k-th `randn_like` (:55), i.e.
+    the noise of timestep T-1-k.  The same noise is used for the 'sum' mix and for the
+    reverse step (F5).  The PNG side effects (:62-66) are not restated.
+    `eps_fn(x_t, t, cond, y)` overrides the UNet (used to check sampler arithmetic alone).
+    """
+    T = s["betas"].shape[0]
+    n = x_T.shape[0]
+    x_t = x_T
+    gt = mask = None
+    if cond is not None and cond_type == "sum":
+        gt, mask = cond[:n, :3], cond[:n, 3][:, None]
+        cond = None
+    for k, i in enumerate(range(T - 1, -1, -1)):
+        noise = noise_tape[k]
+        t = torch.tensor([i for _ in range(n)]).to(x_t.device)
+        if cond_type == "sum":
+            x_t = sum_mix(s, x_t, gt, mask, t, noise)
+        if eps_fn is not None:
+            pred = eps_fn(x_t, t, cond, y)
+        else:
+            pred = unet_forward(sd, cfg, x_t, t, cond=cond, y=y)
+        if record is not None:
+            record.append((i, x_t.clone(), pred.clone()))
+        step = reverse_step_clip if clipped else reverse_step_noclip
+        x_t = step(s, x_t, t, noise, pred)
+    return x_t
+
+
+# --------------------------------------------------------------------------------------
+# DDIM (diffusion/ddim.py, diffusion/util.py)
+# --------------------------------------------------------------------------------------
+
+def ddim_timesteps(S: int, T: int, discretize: str = "uniform") -> np.ndarray:
+    """make_ddim_timesteps (util.py:63-77) and the T/S<2 adjustment (ddim.py:27)."""
+    if discretize == "uniform":
+        c = T // S
+        ts = np.asarray(list(range(0, T, c)))
+    elif discretize == "quad":
+        ts = ((np.linspace(0, np.sqrt(T * .8), S)) ** 2).astype(int)
+    else:
+        raise NotImplementedError(discretize)
+    ts = ts + 1
+    if T / S < 2:
+        ts = ts - 1
+    return ts
+
+
+def ddim_tables(alphas_cumprod: Tensor, ts: np.ndarray, eta: float) -> dict:
+    """make_ddim_sampling_parameters (util.py:80-91) + ddim.py:44-50, with the reference's
+    dtype quirks (F8): `alphas` fp32 tensor, `alphas_prev` float64 ndarray, `sigmas`
+    float64 tensor, `sqrt_one_minus_alphas` fp32 tensor."""
+    alphacums = alphas_cumprod.cpu()
+    alphas = alphacums[ts]
+    alphas_prev = np.asarray([alphacums[0]] + alphacums[ts[:-1]].tolist())
+    sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
+    return {
+        "ddim_timesteps": ts,
+        "ddim_alphas": alphas,
+        "ddim_alphas_prev": alphas_prev,
+        "ddim_sigmas": sigmas,
+        "ddim_sqrt_one_minus_alphas": np.sqrt(1. - alphas),
+    }
+
+
+def ddim_step(tab: dict, index: int, x: Tensor, e_t: Tensor, noise: Optional[Tensor],
+              temperature: float = 1.) -> Tuple[Tensor, Tensor]:
+    """p_sample_ddim after the UNet call (ddim.py:187-207).  `noise` is the
+    `noise_like` draw (:203); None means zeros (exact when sigma_t == 0)."""
+    b, dev = x.shape[0], x.device
+    a_t = torch.full((b, 1, 1, 1), tab["ddim_alphas"][index], device=dev)
+    a_prev = torch.full((b, 1, 1, 1), tab["ddim_alphas_prev"][index], device=dev)
+    sigma_t = torch.full((b, 1, 1, 1), tab["ddim_sigmas"][index], device=dev)
+    somat = torch.full((b, 1, 1, 1), tab["ddim_sqrt_one_minus_alphas"][index], device=dev)
+    pred_x0 = (x - somat * e_t) / a_t.sqrt()
+    dir_xt = (1. - a_prev - sigma_t ** 2).sqrt() * e_t
+    if noise is None:
+        noise = torch.zeros_like(x)
+    nz = sigma_t * noise * temperature
+    x_prev = a_prev.sqrt() * pred_x0 + dir_xt + nz
+    return x_prev, pred_x0
+
+
+@torch.no_grad()
+def ddim_sample(sd: dict, cfg: dict, s: dict, S: int, x_T: Tensor,
+                noise_tape: Optional[Sequence[Tensor]] = None, eta: float = 0.,
+                cond: Optional[Tensor] = None, temperature: float = 1.,
+                log_every_t: int = 100, record: Optional[list] = None, eps_fn=None):
+    """DDIMSampler.sample / ddim_sampling (ddim.py:57-164), mask branch excluded (broken
+    in the reference, F7), CFG excluded.  `noise_tape[i]` is the `noise_like` draw of
+    loop iteration i (the `randn_like` at :171 is drawn and discarded by the reference)."""
+    T = s["betas"].shape[0]
+    ts = ddim_timesteps(S, T)
+    tab = ddim_tables(s["alphas_cumprod"], ts, eta)
+    img = x_T
+    b = img.shape[0]
+    inter = {"x_inter": [img], "pred_x0": [img]}
+    total = ts.shape[0]
+    for i, step in enumerate(np.flip(ts)):
+        index = total - i - 1
+        t = torch.full((b,), int(step), device=img.device, dtype=torch.long)
+        if eps_fn is not None:
+            e_t = eps_fn(img, t, cond, None)
+        else:
+            e_t = unet_forward(sd, cfg, img, t, cond=cond)
+        if record is not None:
+            record.append((int(step), img.clone(), e_t.clone()))
+        nz = None if noise_tape is None else noise_tape[i]
+        img, pred_x0 = ddim_step(tab, index, img, e_t, nz, temperature)
+        if index % log_every_t == 0 or index == total - 1:
+            inter["x_inter"].append(img)
+            inter["pred_x0"].append(pred_x0)
+    return img, inter
+
+
+# --------------------------------------------------------------------------------------
+# fixtures: non-degenerate weights and synthetic inputs
+# --------------------------------------------------------------------------------------
+
+def dezero_(model: torch.nn.Module, seed: int = 4321) -> torch.nn.Module:
+    """The reference zero-initialises 35 convs so a fresh UNet outputs exactly 0 (F2).
+    Re-randomise, under `seed`, every Conv whose weight is all-zero (in named_modules()
+    order, via its own reset_parameters()), and perturb every GroupNorm's affine params
+    (weight = 1 + 0.1 N(0,1), bias = 0.1 N(0,1)) so the affine path is exercised.
+    Works on the reference UNetModel and on the drop-in alike (same module types)."""
+    g = torch.Generator().manual_seed(seed)
+    state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    try:
+        for _, m in model.named_modules():
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.Conv2d)) and not bool(m.weight.any()):
+                m.reset_parameters()
+        for _, m in model.named_modules():
+            if isinstance(m, torch.nn.GroupNorm):
+                with torch.no_grad():
+                    m.weight.copy_(1 + 0.1 * torch.randn(m.weight.shape, generator=g))
+                    m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+    finally:
+        torch.random.set_rng_state(state)
+    return model
+
+
+def synth_cond_sum(n: int, size: int, seed: int) -> Tensor:
+    """cond = cat(gt, mask): gt ~ U[0,1) (data range of data_load.py:438), mask = 1 over
+    the image with one random zeroed rectangle per sample covering 10-40 % per side
+    (script_utils/utils.py:17-37 makes such rectangles; inference.py:101 passes 1-mask)."""
+    g = torch.Generator().manual_seed(seed)
+    gt = torch.rand((n, 3, size, size), generator=g)
+    mask = torch.ones((n, 1, size, size))
+    for i in range(n):
+        hh = int(size * (0.1 + 0.3 * float(torch.rand((), generator=g))))
+        ww = int(size * (0.1 + 0.3 * float(torch.rand((), generator=g))))
+        y0 = int((size - hh) * float(torch.rand((), generator=g)))
+        x0 = int((size - ww) * float(torch.rand((), generator=g)))
+        mask[i, :, y0:y0 + hh, x0:x0 + ww] = 0.
+    return torch.cat([gt, mask], 1)
+
+
+def noise_tape(shape: Tuple[int, ...], steps: int, seed: int) -> Tuple[Tensor, List[Tensor]]:
+    """x_T followed by `steps` standard-normal draws, in the reference's draw order (F6)."""
+    g = torch.Generator().manual_seed(seed)
+    x_T = torch.randn(shape, generator=g)
+    return x_T, [torch.randn(shape, generator=g) for _ in range(steps)]
+
+
+def rel_l2(a: Tensor, b: Tensor) -> float:
+    a = a.double().flatten()
+    b = b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
