@@ -1,0 +1,74 @@
+// Shared helpers for libeo_b200: error plumbing, small device utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+
+#include "../../include/eo_b200.h"
+
+namespace eo {
+
+// thread-local last-error message (eo_last_error)
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define EO_CHECK_CUDA(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      eo::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                    __LINE__);                                                           \
+      return EO_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define EO_REQUIRE(cond, code, ...)                                                      \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      eo::set_error(__VA_ARGS__);                                                        \
+      return (code);                                                                     \
+    }                                                                                    \
+  } while (0)
+
+// checks the kernel launch that just happened
+#define EO_CHECK_LAUNCH()                                                                \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      eo::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),          \
+                    __FILE__, __LINE__);                                                 \
+      return EO_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int num_sms();  // SM count of the current device (cached)
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// accurate variant for the fp32 parity mode
+__device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace eo

@@ -1,0 +1,159 @@
+// Host-side launch interface of every kernel in libeo_b200 (one translation unit per
+// kernel family).  All launches are asynchronous on the given stream and return EO_OK or
+// a negative error code with eo::set_error() filled in.
+#pragma once
+#include "common.cuh"
+
+namespace eo {
+
+enum DType { DT_F32 = 0, DT_BF16 = 1 };
+inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+// ---------------------------------------------------------------------------------------
+// generic SIMT implicit-GEMM convolution (fp32 FFMA).  Used for every conv of the fp32
+// parity mode, and for the stem conv of the bf16 mode.
+// ---------------------------------------------------------------------------------------
+struct ConvSrc {
+  const void* ptr = nullptr;   // NHWC activation of dtype `dt`, or NCHW fp32 if nchw
+  int C = 0;                   // channels of this source
+  int ksize = 3;               // 1 or 3 (pad = ksize/2)
+  int dt = DT_F32;
+  int nchw = 0;
+  const float* gn_scale = nullptr;  // [B, C] (GroupNorm folded to x*scale+shift) or null
+  const float* gn_shift = nullptr;
+  int gn_ld = 0;               // row pitch of gn_scale / gn_shift (total channels of the GroupNorm)
+  int silu = 0;                // SiLU after the affine
+  int w_off = 0;               // first row (k index) of this source in the packed weights
+};
+
+struct ConvSimtParams {
+  ConvSrc src[3];
+  int nsrc = 0;
+  int B = 0, Hin = 0, Win = 0;   // source spatial size (before `up`)
+  int Hout = 0, Wout = 0;
+  int stride = 1;                // 1 or 2 (3x3 sources only)
+  int up = 0;                    // nearest x2 upsample of the sources before the conv
+  const float* W = nullptr;      // packed [Ktot][Cout] fp32
+  int Ktot = 0, Cout = 0;
+  const float* bias = nullptr;     // [Cout] or null
+  const float* bias_nc = nullptr;  // [B, ld_bias_nc] per-sample vector or null
+  int ld_bias_nc = 0;
+  const void* residual = nullptr;  // NHWC [B,Hout,Wout,Cout] dtype out_dt, or null
+  void* out = nullptr;
+  int out_dt = DT_F32;
+  int out_nchw = 0;              // write NCHW fp32 (final eps)
+};
+int launch_conv_simt(const ConvSimtParams& p, cudaStream_t st);
+
+// out conv of the bf16 mode: GN+SiLU folded on load, tiny Cout (<=16), NHWC in (any dtype),
+// NCHW fp32 out.  Bandwidth kernel (arithmetic intensity ~26 flop/B).
+struct ConvSmallNParams {
+  const void* x = nullptr; int dt = DT_BF16;
+  const float* gn_scale = nullptr; const float* gn_shift = nullptr;  // [B, C]
+  int B = 0, H = 0, W = 0, C = 0, Cout = 0;
+  const float* Wp = nullptr;   // packed [9*C][Cout] fp32
+  const float* bias = nullptr; // [Cout]
+  float* out_nchw = nullptr;
+};
+int launch_conv_small_n(const ConvSmallNParams& p, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// GroupNorm(32 groups, eps 1e-5) over one or two NHWC sources (channel concat)
+// ---------------------------------------------------------------------------------------
+struct GnSrc { const void* ptr = nullptr; int C = 0; };
+// sums[B][32][2] (double; sum, sum of squares) must be zero on entry
+int launch_gn_stats(const GnSrc* src, int nsrc, int dt, int B, int HW, double* sums,
+                    cudaStream_t st);
+// scale[b,c] = rstd*gamma[c]; shift[b,c] = beta[c] - mean*rstd*gamma[c]   (C = total channels)
+int launch_gn_finalize(const double* sums, const float* gamma, const float* beta, int B, int C,
+                       int HW, float* scale, float* shift, cudaStream_t st);
+// dst[b,p,off_s + c] = act(src_s[b,p,c]*scale[b,off_s+c] + shift[b,off_s+c])   (bf16 -> bf16)
+int launch_gn_apply(const GnSrc* src, int nsrc, int B, int HW, const float* scale,
+                    const float* shift, int silu, void* dst, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// timestep embedding + small linears (always fp32)
+// ---------------------------------------------------------------------------------------
+// out[b, j] = cos(t_b * freqs[j]) (j < half), sin(...) (half <= j < 2*half)
+int launch_sinusoid(const int64_t* t, const float* freqs, int B, int half, float* out,
+                    cudaStream_t st);
+// out[b,n] = bias[n] + (bias2 ? bias2[n] : 0) + (emb_rows ? emb_rows[idx[b]*N + n] : 0)
+//            + sum_k W[n,k] * act(in[b,k])          (W row-major [N][K], as nn.Linear)
+int launch_linear(const float* in, const float* W, const float* bias, const float* bias2,
+                  const float* emb_rows, const int64_t* idx, int silu_in, int B, int K, int N,
+                  float* out, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// attention, fp32 SIMT (parity mode).  qkv is [B,T,ld] with q/k/v of head h at channel
+// offsets h*head_stride + {0,1,2}*part_stride.  out is [B,T,heads*ch].
+// ---------------------------------------------------------------------------------------
+int launch_attention_simt(const float* qkv, float* out, int B, int T, int heads, int ch,
+                          int ld, int head_stride, int part_stride, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// layout pre-passes of the bf16 mode (bandwidth kernels, 16-byte vectors)
+// ---------------------------------------------------------------------------------------
+// dst[b,2h+i,2w+j,c] = src[b,h,w,c]
+int launch_upsample2x(const void* src, void* dst, int B, int H, int W, int C, cudaStream_t st);
+// dst[(hp*2+wp)][b][h2][w2][c] = src[b][2*h2+hp][2*w2+wp][c]; planes are Bstride images apart
+int launch_space_to_depth(const void* src, void* dst, int B, int Bstride, int H, int W, int C,
+                          cudaStream_t st);
+// generic NHWC (dt) -> NCHW fp32 copy, for eo_unet_read_activation
+int launch_nhwc_to_nchw_f32(const void* src, int dt, float* dst, int B, int HW, int C,
+                            cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// weight packing (run once at finalize)
+// ---------------------------------------------------------------------------------------
+// Packs torch conv weights w[Cout][Cin_total][k][k] (fp32) into a GEMM operand whose K axis
+// is ordered (source segment, tap, channel).  One call per segment:
+//   dst[n*stride_n + (k_off + tap*C + c)*stride_k] = scale * w[row(n)][cin_off + c][tap]
+// row(n) = row_map ? row_map[n] : n  (row_map[n] < 0 -> zero row); n in [0, Nout).
+// If tap_fold (upsample sub-pixel folding) is non-null it is unused here (see engine).
+int launch_pack_conv_weight(const float* w, int Cin_total, int ksize, int cin_off, int C,
+                            void* dst, int dst_dt, long long stride_n, long long stride_k,
+                            int k_off, int Nout, const int* row_map, cudaStream_t st);
+// dst[n] = (a ? a[row(n)] : 0) + (b ? b[row(n)] : 0)
+int launch_pack_bias(const float* a, const float* b, float* dst, int Nout, const int* row_map,
+                     cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// tcgen05 tensor-core kernels (tc_conv.cu / tc_attn.cu)
+// ---------------------------------------------------------------------------------------
+struct TcConvSeg {
+  const void* ptr = nullptr;  // bf16 NHWC [Bt, H, W, C]  (Bt may be 4*B for space-to-depth planes)
+  int C = 0;
+  int Bt = 0;
+  int ntaps = 0;              // number of taps taken from this segment
+  int8_t dh[9], dw[9];        // spatial shift of each tap (in this segment's grid)
+  int dn[9];                  // batch-coordinate shift of each tap (plane select)
+};
+struct TcConvParams {
+  TcConvSeg seg[3];
+  int nseg = 0;
+  int B = 0, H = 0, W = 0;      // OUTPUT grid (== segment grid; stride/upsample are pre-passes)
+  const void* Wp = nullptr;     // bf16 [Cout_pad][Ktot], K contiguous, K ordered (seg, tap, c)
+  int Ktot = 0, Cout = 0;       // Cout: multiple of 64
+  const float* bias = nullptr;      // [Cout] or null
+  const float* bias_nc = nullptr;   // [B, ld_bias_nc] or null
+  int ld_bias_nc = 0;
+  const void* residual = nullptr;   // bf16 NHWC [B,H,W,Cout] or null
+  void* out = nullptr;              // bf16 NHWC [B,H,W,Cout]
+};
+// A prepared launch (tensor maps encoded once at plan time)
+struct TcConvPlan;
+int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out);
+void tc_conv_plan_destroy(TcConvPlan* p);
+int tc_conv_launch(const TcConvPlan* plan, int B, cudaStream_t st);
+
+struct TcAttnParams {
+  const void* qkv = nullptr;  // bf16 [B, T, heads*3*64]: per head q|k|v each padded to 64 channels
+  void* out = nullptr;        // bf16 [B, T, heads*ch]
+  int B = 0, T = 0, heads = 0, ch = 0;  // ch <= 64
+};
+struct TcAttnPlan;
+int tc_attn_plan_create(const TcAttnParams& p, TcAttnPlan** out);
+void tc_attn_plan_destroy(TcAttnPlan* p);
+int tc_attn_launch(const TcAttnPlan* plan, int B, cudaStream_t st);
+
+}  // namespace eo

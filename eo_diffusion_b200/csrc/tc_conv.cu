@@ -1,0 +1,357 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators
+// in TMEM, operands staged by TMA).  bf16 operands, fp32 accumulate.
+//
+// Replaces, for the bf16 mode, every nn.Conv2d 3x3 / 1x1 and nn.Conv1d k=1 on the UNet
+// path (reference backbones/unet_openai.py: ResBlock :316,:342,:353; AttentionBlock qkv/
+// proj_out :412,:422; Downsample :262; Upsample :227), with the adds that follow them
+// (`h + emb_out` :382, `skip_connection(x) + h` :385, `x + h` :433) in the epilogue, the
+// 1x1 skip convolution as extra K blocks of the same accumulator, and th.cat (:773) as a
+// second K segment.
+//
+// GEMM view:  D[M = pixels, N = Cout] = sum_k A[M, k] * Wp[N, k],  k = (segment, tap, channel)
+//   A tile  : 128 output pixels = a (bn x bh x bw) box of the NHWC activation; for tap
+//             (dh, dw) the SAME box shifted by (dh, dw) is fetched by one 4-D tiled TMA
+//             load; out-of-bounds rows/columns are zero-filled by the TMA unit, which is
+//             exactly the conv's zero padding.  64 channels (128 B) per K block, 128B swizzle.
+//   B tile  : BN x 64 slice of the packed weights Wp[Cout][Ktot] (K contiguous), 2-D TMA.
+//   D       : 128 lanes x BN fp32 columns of TMEM.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one
+// elected lane), warps 2..5 = epilogue (each owns the TMEM lane quadrant warp_id % 4).
+// Two CTAs are co-resident per SM (<= 96 KB smem and <= 256 TMEM columns each) so that one
+// CTA's epilogue overlaps the other's main loop.
+//
+// Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2 * M * Cout * Ktot.
+#include "kernels.h"
+#include "tc_common.cuh"
+#include <vector>
+
+namespace eo {
+
+namespace {
+
+struct KBlk { int seg; int c0; int dh_dw; int dn; };   // dh: low 16 bits, dw: high 16 bits
+
+struct TileGeom {
+  int bw, bh, bn;          // box extents, bw*bh*bn == 128
+  int tiles_w, tiles_h;
+  int H, W;
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = STAGES * A_BYTES;
+  static constexpr int TAB_OFF = B_OFF + STAGES * B_BYTES;
+  static constexpr int MAX_KB = 192;
+  static constexpr int BAR_OFF = TAB_OFF + MAX_KB * 16;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for manual 1024 B alignment
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 2)
+k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+          const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
+          const KBlk* __restrict__ kblks, int nkb, TileGeom g, int B,
+          const float* __restrict__ bias, const float* __restrict__ bias_nc, int ld_bias_nc,
+          const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, int Cout) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
+  KBlk* tab = reinterpret_cast<KBlk*>(smem + L::TAB_OFF);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&mapA0);
+    tc::tma_prefetch_desc(&mapB);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_ptr, BN);
+    tc::tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < nkb; i += blockDim.x) tab[i] = kblks[i];
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // tile coordinates
+  const int mt = blockIdx.x;
+  const int tw = mt % g.tiles_w;
+  const int th = (mt / g.tiles_w) % g.tiles_h;
+  const int nt = mt / (g.tiles_w * g.tiles_h);
+  const int w0 = tw * g.bw, h0 = th * g.bh, n0 = nt * g.bn;
+  const int nbase = blockIdx.y * BN;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        tc::mbar_wait(&empty[s], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&full[s], A_BYTES + L::B_BYTES);
+        const KBlk e = tab[kb];
+        const int dh = (int)(short)(e.dh_dw & 0xffff), dw = (int)(short)(e.dh_dw >> 16);
+        const CUtensorMap* ma = e.seg == 0 ? &mapA0 : (e.seg == 1 ? &mapA1 : &mapA2);
+        tc::tma_load_4d(smem + L::A_OFF + s * A_BYTES, ma, &full[s], e.c0, w0 + dw, h0 + dh,
+                        n0 + e.dn);
+        tc::tma_load_2d(smem + L::B_OFF + s * L::B_BYTES, &mapB, &full[s], kb * BK, nbase);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN, 0, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        tc::mbar_wait(&full[s], ph);
+        tc::tc_fence_after();
+        const uint64_t adesc = tc::make_sw128_desc(tc::smem_u32(smem + L::A_OFF + s * A_BYTES));
+        const uint64_t bdesc = tc::make_sw128_desc(tc::smem_u32(smem + L::B_OFF + s * L::B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          tc::umma_f16_ss(tmem_base, tc::desc_advance(adesc, k * 32), tc::desc_advance(bdesc, k * 32),
+                          idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(&empty[s]);       // frees the smem stage when these MMAs retire
+      }
+      tc::umma_commit(tmem_full);         // accumulator complete
+    }
+  } else {
+    // ---- epilogue: TMEM -> registers -> (+bias, +per-sample bias, +residual) -> bf16 -> HBM
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ww = row % g.bw;
+    const int hh = (row / g.bw) % g.bh;
+    const int nn = row / (g.bw * g.bh);
+    const int n_img = n0 + nn;
+    const bool valid = n_img < B;
+    const long long pix = ((long long)n_img * g.H + (h0 + hh)) * g.W + (w0 + ww);
+    const float* bnc = (bias_nc && valid) ? bias_nc + (long long)n_img * ld_bias_nc : nullptr;
+    tc::mbar_wait(tmem_full, 0);
+    tc::tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tc::tmem_ld_wait();
+      const int n = nbase + c0;
+      if (valid && n < Cout) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + j));
+            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+          }
+        }
+        if (bnc) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = __ldg(reinterpret_cast<const float4*>(bnc + n + j));
+            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+          }
+        }
+        const long long o = pix * Cout + n;
+        if (residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(residual + o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 r = __ldg(rp + j);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 t = __bfloat1622float2(h2[e]);
+              f[j * 8 + e * 2] += t.x; f[j * 8 + e * 2 + 1] += t.y;
+            }
+          }
+        }
+        uint4* op = reinterpret_cast<uint4*>(out + o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 w;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            h2[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+          op[j] = w;
+        }
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, BN);
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_encodeTiled fn = get_encode_fn();
+  EO_REQUIRE(fn != nullptr, EO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t d[5]; cuuint64_t s[4]; cuuint32_t b[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                  d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EO_REQUIRE(r == CUDA_SUCCESS, EO_ERR_CUDA,
+             "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
+             (int)r, rank, (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0),
+             (unsigned long long)(rank > 2 ? d[2] : 0), (unsigned long long)(rank > 3 ? d[3] : 0),
+             b[0], rank > 1 ? b[1] : 0, rank > 2 ? b[2] : 0, rank > 3 ? b[3] : 0);
+  return EO_OK;
+}
+
+struct TcConvPlan {
+  CUtensorMap mapA[3];
+  CUtensorMap mapB;
+  KBlk* d_kblks = nullptr;
+  int nkb = 0;
+  TileGeom g{};
+  int bn_tile = 128;
+  TcConvParams p;
+};
+
+static int floor_pow2(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
+
+int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out) {
+  EO_REQUIRE(p.nseg >= 1 && p.nseg <= 3, EO_ERR_ARG, "tc_conv: nseg");
+  EO_REQUIRE(p.Cout % 64 == 0, EO_ERR_ARG, "tc_conv: Cout %d must be a multiple of 64", p.Cout);
+  TcConvPlan* pl = new TcConvPlan();
+  pl->p = p;
+  // ---- tile geometry: 128 pixels = bn x bh x bw
+  TileGeom g;
+  g.H = p.H; g.W = p.W;
+  g.bw = floor_pow2(p.W < 16 ? p.W : 16);
+  g.bh = floor_pow2(p.H < BM / g.bw ? p.H : BM / g.bw);
+  g.bn = BM / (g.bw * g.bh);
+  if (p.W % g.bw != 0 || p.H % g.bh != 0) {
+    delete pl;
+    set_error("tc_conv: feature map %dx%d is not tileable by %dx%d boxes", p.H, p.W, g.bh, g.bw);
+    return EO_ERR_ARG;
+  }
+  g.tiles_w = p.W / g.bw; g.tiles_h = p.H / g.bh;
+  pl->g = g;
+  pl->bn_tile = (p.Cout % 256 == 0) ? 256 : 128;
+  // ---- K-block table and activation maps
+  std::vector<KBlk> tab;
+  for (int s = 0; s < p.nseg; ++s) {
+    const TcConvSeg& sg = p.seg[s];
+    if (sg.C % BK != 0) {
+      delete pl;
+      set_error("tc_conv: segment channels %d must be a multiple of 64", sg.C);
+      return EO_ERR_ARG;
+    }
+    uint64_t dims[4] = {(uint64_t)sg.C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)sg.Bt};
+    uint64_t str[3] = {(uint64_t)sg.C * 2, (uint64_t)p.W * sg.C * 2, (uint64_t)p.H * p.W * sg.C * 2};
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)g.bw, (uint32_t)g.bh, (uint32_t)g.bn};
+    int rc = encode_tmap_bf16(&pl->mapA[s], sg.ptr, 4, dims, str, box);
+    if (rc != EO_OK) { delete pl; return rc; }
+    for (int t = 0; t < sg.ntaps; ++t)
+      for (int c0 = 0; c0 < sg.C; c0 += BK) {
+        KBlk e;
+        e.seg = s; e.c0 = c0;
+        e.dh_dw = ((int)sg.dh[t] & 0xffff) | ((int)sg.dw[t] << 16);
+        e.dn = sg.dn[t];
+        tab.push_back(e);
+      }
+  }
+  for (int s = p.nseg; s < 3; ++s) pl->mapA[s] = pl->mapA[0];
+  pl->nkb = (int)tab.size();
+  if (pl->nkb * BK != p.Ktot || pl->nkb > 192) {
+    delete pl;
+    set_error("tc_conv: K blocks %d inconsistent with Ktot %d (max 192 blocks)", pl->nkb, p.Ktot);
+    return EO_ERR_ARG;
+  }
+  {
+    int cout_pad = (int)ceil_div(p.Cout, pl->bn_tile) * pl->bn_tile;
+    (void)cout_pad;
+    uint64_t dims[2] = {(uint64_t)p.Ktot, (uint64_t)p.Cout};
+    uint64_t str[1] = {(uint64_t)p.Ktot * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)pl->bn_tile};
+    int rc = encode_tmap_bf16(&pl->mapB, p.Wp, 2, dims, str, box);
+    if (rc != EO_OK) { delete pl; return rc; }
+  }
+  cudaError_t e = cudaMalloc(&pl->d_kblks, tab.size() * sizeof(KBlk));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(pl->d_kblks, tab.data(), tab.size() * sizeof(KBlk), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("tc_conv: K-block table upload failed: %s", cudaGetErrorString(e));
+    tc_conv_plan_destroy(pl);
+    return EO_ERR_CUDA;
+  }
+  *out = pl;
+  return EO_OK;
+}
+
+void tc_conv_plan_destroy(TcConvPlan* p) {
+  if (!p) return;
+  if (p->d_kblks) cudaFree(p->d_kblks);
+  delete p;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const TcConvPlan* pl, int B, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<BN, STAGES>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    attr_set = true;
+  }
+  const TileGeom& g = pl->g;
+  int tiles_n = (int)ceil_div(B, g.bn);
+  dim3 grid((unsigned)(g.tiles_w * g.tiles_h * tiles_n), (unsigned)ceil_div(pl->p.Cout, BN));
+  k_conv_tc<BN, STAGES><<<grid, 192, L::DYN_BYTES, st>>>(
+      pl->mapA[0], pl->mapA[1], pl->mapA[2], pl->mapB, pl->d_kblks, pl->nkb, g, B, pl->p.bias,
+      pl->p.bias_nc, pl->p.ld_bias_nc, reinterpret_cast<const __nv_bfloat16*>(pl->p.residual),
+      reinterpret_cast<__nv_bfloat16*>(pl->p.out), pl->p.Cout);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+
+int tc_conv_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
+  if (pl->bn_tile == 256) return launch_tc<256, 2>(pl, B, st);
+  return launch_tc<128, 3>(pl, B, st);
+}
+
+}  // namespace eo

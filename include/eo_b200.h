@@ -1,0 +1,215 @@
+/*
+ * eo_b200.h -- C ABI of libeo_b200.so, the B200 (sm_100a) implementation of
+ * EO_Diffusion's reverse-sampling hot path.
+ *
+ * The reference (furio1999/EO_Diffusion) has no FFI: its "operator API" for this path is
+ * three Python classes.  Each entry point below replaces the body of one reference
+ * method; the Python host in eo_diffusion_b200/ keeps the reference signatures and calls
+ * these through ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; device pointers are raw CUDA device addresses; `stream` is a
+ *     cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every call only ENQUEUES work on `stream` (no device-wide synchronisation), except
+ *     eo_unet_finalize which may synchronise `stream` once while packing weights;
+ *   - return value 0 = success, negative = error; eo_last_error() returns a thread-local
+ *     message for the last failing call on this thread.  The library never aborts;
+ *   - image tensors at the boundary are the reference's: NCHW, contiguous, fp32;
+ *     timesteps are int64 (reference: diffusion/model.py:56);
+ *   - there is no CPU fallback: every entry point requires a CUDA device of compute
+ *     capability 10.x and fails with EO_ERR_DEVICE otherwise.
+ */
+#ifndef EO_B200_H
+#define EO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EO_API __attribute__((visibility("default")))
+#else
+#define EO_API
+#endif
+
+#define EO_OK 0
+#define EO_ERR_ARG (-1)     /* bad argument / unsupported configuration            */
+#define EO_ERR_CUDA (-2)    /* a CUDA runtime or driver call failed                */
+#define EO_ERR_STATE (-3)   /* call order violated (e.g. forward before finalize)  */
+#define EO_ERR_DEVICE (-4)  /* no sm_100 device                                    */
+#define EO_ERR_KEY (-5)     /* unknown state-dict key / shape mismatch             */
+
+/* arithmetic mode of the UNet internals; the sampler state is always fp32 */
+#define EO_MODE_FP32 0 /* fp32 activations + fp32 FFMA kernels (parity mode, rel-L2 <= 1e-4) */
+#define EO_MODE_BF16 1 /* bf16 activations, tcgen05 tensor-core kernels, fp32 accumulate     */
+
+EO_API const char* eo_last_error(void);
+EO_API int eo_version(void);
+/* 0 if the current CUDA device is usable (sm_100), EO_ERR_DEVICE otherwise */
+EO_API int eo_device_check(void);
+
+/* ------------------------------------------------------------------------------------
+ * UNet: replaces UNetModel.forward (backbones/unet_openai.py:746-780) and everything it
+ * calls (ResBlock :365-385, AttentionBlock :427-433, QKVAttentionLegacy :465-481,
+ * QKVAttention :497-515, Downsample :269-271, Upsample :229-242, GroupNorm32 :11-13,
+ * timestep_embedding :81-99, time_embed MLP :597-602).
+ * The configuration mirrors UNetModel.__init__ (unet_openai.py:553-575).
+ * ---------------------------------------------------------------------------------- */
+typedef struct eo_unet eo_unet;
+
+typedef struct eo_unet_cfg {
+  int32_t in_channels;      /* channels of x after the optional concat with cond */
+  int32_t model_channels;
+  int32_t out_channels;
+  int32_t num_res_blocks;
+  int32_t n_attention_resolutions;
+  int32_t attention_resolutions[8];
+  int32_t n_channel_mult;
+  int32_t channel_mult[8];
+  int32_t time_emb_factor;
+  int32_t num_classes;      /* 0 = not class-conditional */
+  int32_t num_heads;
+  int32_t num_head_channels; /* -1 = use num_heads */
+  int32_t num_heads_upsample; /* -1 = num_heads */
+  int32_t use_new_attention_order;
+  /* options of the reference constructor that this path does not implement; they must
+     hold the values below or eo_unet_create fails with EO_ERR_ARG */
+  int32_t dims;                 /* 2 */
+  int32_t conv_resample;        /* 1 */
+  int32_t use_scale_shift_norm; /* 0 */
+  int32_t resblock_updown;      /* 0 */
+} eo_unet_cfg;
+
+EO_API int eo_unet_create(const eo_unet_cfg* cfg, eo_unet** out);
+EO_API void eo_unet_destroy(eo_unet* u);
+
+/* Number of state-dict entries the engine consumes, and their names/shapes, in the
+ * reference's state_dict() order (dead `nout.*` / `conv_out.*` entries, unet_openai.py:744,
+ * are not consumed).  `shape` receives up to 4 extents; returns ndim or negative. */
+EO_API int eo_unet_num_weights(const eo_unet* u);
+EO_API const char* eo_unet_weight_name(const eo_unet* u, int index);
+EO_API int eo_unet_weight_shape(const eo_unet* u, int index, int64_t shape[4]);
+
+/* Hand one fp32, contiguous, device-resident parameter to the engine under its reference
+ * state-dict key (e.g. "input_blocks.1.0.in_layers.2.weight").  The engine copies/repacks
+ * it into kernel layout at finalize; the caller keeps ownership of `dev_ptr`. */
+EO_API int eo_unet_set_weight(eo_unet* u, const char* key, const float* dev_ptr,
+                       const int64_t* shape, int ndim);
+
+/* Pack weights for `mode`, size the activation workspace for batches up to `max_batch`
+ * of H x W images and build the launch plan.  May be called again after weights, mode or
+ * geometry change. */
+EO_API int eo_unet_finalize(eo_unet* u, int mode, int max_batch, int H, int W, void* stream);
+
+/* eps = UNet(cat(x, cond), timesteps[, y]).
+ *   x         [B, Cx, H, W] fp32 NCHW
+ *   cond      [B, Cc, H, W] fp32 NCHW or NULL (Cx + Cc == in_channels; unet_openai.py:754-756)
+ *   timesteps [B] int64, device
+ *   y         [B] int64, device, or NULL (must be non-NULL iff num_classes > 0, :758-760)
+ *   eps_out   [B, out_channels, H, W] fp32 NCHW
+ */
+EO_API int eo_unet_forward(eo_unet* u, const float* x, int Cx, const float* cond, int Cc,
+                    const int64_t* timesteps, const int64_t* y, float* eps_out, int B,
+                    void* stream);
+
+/* Profiling variant of eo_unet_forward used by bench.py's roofline leg: brackets every op of
+ * the launch plan with CUDA events on `stream`, waits for the last one and writes the device
+ * time of op i (milliseconds) to ms_per_op[i], i < eo_unet_num_ops().  eo_unet_op_info names
+ * op i (reference module path), its kernel family, and its ALGORITHMIC FLOPs / HBM bytes
+ * per image (DESIGN.md states the formulas). */
+EO_API int eo_unet_forward_timed(eo_unet* u, const float* x, int Cx, const float* cond, int Cc,
+                          const int64_t* timesteps, const int64_t* y, float* eps_out, int B,
+                          void* stream, float* ms_per_op);
+EO_API int eo_unet_num_ops(const eo_unet* u);
+EO_API int eo_unet_op_info(const eo_unet* u, int index, const char** name, const char** kernel,
+                    double* flops_per_image, double* bytes_per_image);
+
+/* bytes of device memory held by the engine (packed weights + workspace) */
+EO_API int64_t eo_unet_device_bytes(const eo_unet* u);
+/* number of kernel launches one eo_unet_forward enqueues (for bench.py's gpu_launches) */
+EO_API int eo_unet_launches_per_forward(const eo_unet* u);
+
+/* debugging/validation aid used by the parity tests: copy an internal activation
+ * (name = reference module path, e.g. "input_blocks.3") of the LAST forward into `out`
+ * as fp32 NCHW.  Returns element count, or negative if unknown. */
+EO_API int64_t eo_unet_read_activation(eo_unet* u, const char* name, float* out_dev, int64_t capacity,
+                                int B, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * DDPM sampler arithmetic: replaces the elementwise tails of EODiffusion.sampling
+ * (diffusion/model.py:58-60), _forward_diffusion (:94-98), _reverse_diffusion_with_clip
+ * (:133-150) and _reverse_diffusion (:110-122).  Bit-exact with the reference's fp32 op
+ * sequence (no FMA contraction).
+ *
+ * `table` is a device array [T][EO_DDPM_NCOEF] of per-timestep scalars that the host
+ * computes with the reference's own torch op sequence; kernels gather row timesteps[b],
+ * like the reference's `.gather(-1, t)`.
+ * ---------------------------------------------------------------------------------- */
+#define EO_DDPM_NCOEF 12
+#define EO_COEF_SQRT_ACP 0          /* sqrt_alphas_cumprod[t]                       */
+#define EO_COEF_SQRT_1M_ACP 1       /* sqrt_one_minus_alphas_cumprod[t]             */
+#define EO_COEF_SQRT_RECIP_ACP 2    /* sqrt(1/acp[t])                                */
+#define EO_COEF_SQRT_RECIPM1_ACP 3  /* sqrt(1/acp[t] - 1)                            */
+#define EO_COEF_MEAN_X0 4           /* beta*sqrt(acp[t-1])/(1-acp[t])      (t>0)     */
+#define EO_COEF_MEAN_XT 5           /* (1-acp[t-1])*sqrt(alpha)/(1-acp[t]) (t>0)     */
+#define EO_COEF_STD 6               /* sqrt(beta*(1-acp[t-1])/(1-acp[t]))  (t>0)     */
+#define EO_COEF_MEAN_X0_T0 7        /* beta/(1-acp[t])                               */
+#define EO_COEF_RECIP_SQRT_ALPHA 8  /* 1/sqrt(alpha[t])                              */
+#define EO_COEF_EPS_NOCLIP 9        /* (1-alpha[t])/sqrt_one_minus_acp[t]            */
+
+/* x_out = mask*(sa[t]*gt + sb[t]*noise) + (1-mask)*x_t     (model.py:59-60)
+ *   x_t, gt, noise, x_out [B,C,H,W]; mask [B,1,H,W]; x_out may alias x_t */
+EO_API int eo_ddpm_sum_mix(const float* x_t, const float* gt, const float* mask, const float* noise,
+                    const int64_t* timesteps, const float* table, float* x_out, int B, int C,
+                    int HW, void* stream);
+
+/* x_out = posterior_mean(x_t, eps) + std*noise.
+ *   clip != 0: _reverse_diffusion_with_clip, else _reverse_diffusion.
+ *   all_t_positive: the host's evaluation of the reference's `t.min() > 0` (model.py:140). */
+EO_API int eo_ddpm_step(const float* x_t, const float* eps, const float* noise, const int64_t* timesteps,
+                 const float* table, float* x_out, int B, int C, int HW, int clip,
+                 int all_t_positive, void* stream);
+
+/* Fused: the step of timestep t followed by the 'sum' mix of the NEXT iteration
+ * (timesteps_next, noise_next), saving one round trip of x through HBM. */
+EO_API int eo_ddpm_step_mix(const float* x_t, const float* eps, const float* noise,
+                     const int64_t* timesteps, const float* gt, const float* mask,
+                     const float* noise_next, const int64_t* timesteps_next, const float* table,
+                     float* x_out, int B, int C, int HW, int clip, int all_t_positive,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * DDIM step: replaces DDIMSampler.p_sample_ddim after the UNet call (diffusion/ddim.py:
+ * 187-207).  Scalars are the fp32 values the reference materialises with torch.full:
+ *   sqrt_a_t = sqrt(a_t), sqrt_1m_a_t, sqrt_a_prev = sqrt(a_prev),
+ *   dir_coef = sqrt(1 - a_prev - sigma_t^2), sigma_t, temperature.
+ * noise may be NULL when sigma_t == 0.  Writes x_prev and pred_x0 (either may alias x).
+ * ---------------------------------------------------------------------------------- */
+EO_API int eo_ddim_step(const float* x, const float* e_t, const float* noise, float* x_prev,
+                 float* pred_x0, float sqrt_a_t, float sqrt_1m_a_t, float sqrt_a_prev,
+                 float dir_coef, float sigma_t, float temperature, int64_t n_elems,
+                 void* stream);
+
+/* Classifier-free guidance combine e = e_u + s*(e_c - e_u) (ddim.py:180-181). */
+EO_API int eo_cfg_combine(const float* e_uncond, const float* e_cond, float scale, float* e_out,
+                   int64_t n_elems, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Kernel self-tests (used by tests/ on the GPU box): run one tensor-core implicit-GEMM
+ * convolution / one attention call on caller-provided buffers, outside any UNet.
+ * ---------------------------------------------------------------------------------- */
+/* y[B,H,W,Cout] (bf16 NHWC) = conv_kxk(x[B,H,W,Cin] bf16 NHWC, w[Cout,Cin,k,k] fp32) + bias
+ * [+ residual bf16 NHWC]; k in {1,3}, stride 1, pad k/2. */
+EO_API int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const void* residual,
+                    void* y_bf16, int B, int H, int W, int Cin, int Cout, int k, void* stream);
+/* qkv [B,T,3*heads*ch] in the LEGACY channel order (head, {q,k,v}, ch) bf16 ->
+ * out [B,T,heads*ch] bf16 */
+EO_API int eo_test_attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int heads, int ch,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EO_B200_H */

@@ -1,0 +1,175 @@
+"""UNet forward and full sampling trajectories through the drop-in API (-> C ABI -> CUDA)
+against the golden vectors recorded from the live reference and against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): per-step eps relative L2 <= 1e-4 in the fp32 mode and
+<= 1e-2 in the bf16 tensor-core mode; timestep / schedule indexing exact; trajectory
+mean-abs error bounds stated per test.  Needs a B200."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_unet, golden, golden_cfg, rel_l2, replay, tt, weight_checksum
+from eo_diffusion_b200 import DDIMSampler, EODiffusion
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+_models = {}
+
+
+def model_for(g, dev, mode):
+    cfg = golden_cfg(g)
+    key = (json.dumps(cfg, sort_keys=True), mode)
+    if key not in _models:
+        m = build_unet(cfg, int(g["init_seed"]), int(g["dezero_seed"]))
+        assert weight_checksum(m.state_dict()) == json.loads(str(g["wsum"]))["sha256"]
+        _models[key] = m.to(dev).set_compute_mode(mode)
+    return _models[key], cfg
+
+
+@pytest.mark.parametrize("name", ["tiny_eps", "tiny_eps_b3", "tiny_concat_eps", "small_eps",
+                                  "small_ms_concat_eps", "base64_eps", "base64_eps_t500",
+                                  "base64_eps_t1", "base64_eps_t0"])
+def test_eps_fp32_mode(cuda_dev, name):
+    g = golden(name)
+    m, _ = model_for(g, cuda_dev, "fp32")
+    cond = tt(g["cond"]).to(cuda_dev) if "cond" in g else None
+    eps = m(tt(g["x"]).to(cuda_dev), tt(g["t"]).to(cuda_dev), cond=cond)
+    assert eps.shape == g["eps"].shape and eps.dtype == torch.float32
+    err = rel_l2(eps, tt(g["eps"]))
+    assert err <= TOL["fp32"], f"{name}: rel L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("name", ["small_eps", "small_ms_concat_eps", "base64_eps", "base64_eps_t500",
+                                  "base64_eps_t1", "base64_eps_t0"])
+def test_eps_bf16_mode(cuda_dev, name):
+    g = golden(name)
+    m, _ = model_for(g, cuda_dev, "bf16")
+    cond = tt(g["cond"]).to(cuda_dev) if "cond" in g else None
+    eps = m(tt(g["x"]).to(cuda_dev), tt(g["t"]).to(cuda_dev), cond=cond)
+    err = rel_l2(eps, tt(g["eps"]))
+    assert err <= TOL["bf16"], f"{name}: rel L2 {err:.3e}"
+
+
+def test_bf16_mode_rejects_unsupported_width(cuda_dev):
+    g = golden("tiny_eps")          # 32 base channels: not a multiple of the 64-wide K block
+    m, _ = model_for(g, cuda_dev, "bf16")
+    with pytest.raises(RuntimeError, match="model_channels"):
+        m(tt(g["x"]).to(cuda_dev), tt(g["t"]).to(cuda_dev))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_batch_independence_and_replanning(cuda_dev, mode):
+    """Samples are independent (per-sample GroupNorm / attention): a sample's eps does not
+    depend on what else is in the batch, nor on the engine having been planned for a larger
+    batch.  Also exercises re-planning when the batch grows."""
+    g = golden("small_eps")
+    m, cfg = model_for(g, cuda_dev, mode)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn((5, 3, 32, 32), generator=gen).to(cuda_dev)
+    t = torch.tensor([999, 0, 17, 500, 250]).to(cuda_dev)
+    one = m(x[2:3], t[2:3])
+    allb = m(x, t)
+    again = m(x[2:3], t[2:3])
+    tol = 1e-5 if mode == "fp32" else 2e-3
+    assert rel_l2(allb[2:3], one) <= tol
+    assert rel_l2(again, one) <= tol
+
+
+def test_class_conditional_and_new_attention_order(cuda_dev):
+    """label_emb add (unet_openai.py:764-766), num_head_channels, QKVAttention channel order
+    (:497-515) against the oracle on random weights."""
+    cfg = dict(image_size=16, in_channels=4, model_channels=32, out_channels=2, num_res_blocks=1,
+               attention_resolutions=[1, 2], channel_mult=[1, 2], num_heads=2, num_classes=5,
+               num_head_channels=16, use_new_attention_order=True)
+    m = build_unet(cfg, 77, 78)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn((3, 4, 16, 16), generator=gen)
+    t = torch.tensor([0, 999, 400])
+    y = torch.tensor([4, 0, 2])
+    want = O.unet_forward(sd, O.full_cfg(**cfg), x, t, y=y)
+    got = m.to(cuda_dev).set_compute_mode("fp32")(x.to(cuda_dev), t.to(cuda_dev), y=y.to(cuda_dev))
+    assert rel_l2(got, want) <= TOL["fp32"]
+
+
+def test_weights_update_is_picked_up(cuda_dev):
+    """load_state_dict / in-place edits after the first forward re-pack the engine weights."""
+    g = golden("tiny_eps")
+    cfg = golden_cfg(g)
+    m = build_unet(cfg, 1, 2).to(cuda_dev).set_compute_mode("fp32")
+    x, t = tt(g["x"]).to(cuda_dev), tt(g["t"]).to(cuda_dev)
+    first = m(x, t)
+    good = build_unet(cfg, int(g["init_seed"]), int(g["dezero_seed"]))
+    m.load_state_dict(good.state_dict())
+    second = m(x, t)
+    assert rel_l2(first, tt(g["eps"])) > 1e-2
+    assert rel_l2(second, tt(g["eps"])) <= TOL["fp32"]
+
+
+def _run_ddpm(g, dev, mode, cond_type, clipped, tmp_path):
+    m, cfg = model_for(g, dev, mode)
+    T, n = int(g["T"]), int(g["n"])
+    size = cfg["image_size"]
+    d = EODiffusion(m, size, 3, timesteps=T, cond_type=cond_type).to(dev)
+    x_T, tape = O.noise_tape((n, 3, size, size), T, seed=int(g["tape_seed"]))
+    cond = tt(g["cond"]) if "cond" in g else None
+    rec = []
+    h = m.register_forward_hook(lambda mod, args, kw, out: rec.append(
+        (int(args[1][0]), args[0].detach().clone(), out.detach().clone())), with_kwargs=True)
+    try:
+        with replay([x_T], tape, tmp_cwd=str(tmp_path)):
+            out = d.sampling(n, clipped_reverse_diffusion=clipped, device=dev, cond=cond)
+    finally:
+        h.remove()
+    return out, rec
+
+
+def test_tiny_ddpm_sum_trajectory_fp32(cuda_dev, tmp_path):
+    g = golden("tiny_ddpm_sum_T8")
+    out, rec = _run_ddpm(g, cuda_dev, "fp32", "sum", True, tmp_path)
+    assert [r[0] for r in rec] == list(g["t_seq"])                 # timestep sequence exact
+    assert torch.equal(rec[0][1].cpu(), tt(g["xt_step0"]))         # first mixed state bit-exact
+    assert rel_l2(rec[0][2], tt(g["eps_step0"])) <= TOL["fp32"]
+    assert rel_l2(rec[3][2], tt(g["eps_step3"])) <= 5e-4           # inputs have drifted by then
+    mae = float((out.cpu() - tt(g["x0"])).abs().mean())
+    assert mae <= 1e-3, mae                                        # stated fp32 trajectory bound
+
+
+def test_tiny_ddpm_uncond_noclip_trajectory_fp32(cuda_dev, tmp_path):
+    g = golden("tiny_ddpm_none_T8_noclip")
+    out, rec = _run_ddpm(g, cuda_dev, "fp32", None, False, tmp_path)
+    assert [r[0] for r in rec] == list(g["t_seq"])
+    assert rel_l2(rec[0][2], tt(g["eps_step0"])) <= TOL["fp32"]
+    # un-clipped early steps amplify eps by sqrt(1/alpha_bar - 1) ~ 1e4: relative, not absolute
+    assert rel_l2(out, tt(g["x0"])) <= 5e-3
+
+
+@pytest.mark.parametrize("mode,mae_tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_base64_ddpm_sum_trajectory(cuda_dev, tmp_path, mode, mae_tol):
+    """BASELINE config 1 (64x64, batch 1, 'sum', clipped) over a 20-step schedule."""
+    g = golden("base64_ddpm_sum_T20")
+    out, rec = _run_ddpm(g, cuda_dev, mode, "sum", True, tmp_path)
+    assert [r[0] for r in rec] == list(g["t_seq"])
+    assert torch.equal(rec[0][1].cpu(), tt(g["xt_step0"]))
+    assert rel_l2(rec[0][2], tt(g["eps_step0"])) <= TOL[mode]
+    mae = float((out.cpu() - tt(g["x0"])).abs().mean())
+    assert mae <= mae_tol, mae
+
+
+@pytest.mark.parametrize("eta", [0.0, 0.5])
+def test_tiny_ddim_trajectory_fp32(cuda_dev, eta):
+    g = golden(f"tiny_ddim_S4_T8_eta{eta}")
+    m, cfg = model_for(g, cuda_dev, "fp32")
+    d = EODiffusion(m, 16, 3, timesteps=8).to(cuda_dev)
+    smp = DDIMSampler(d)
+    n = int(g["n"])
+    x_T, tape = O.noise_tape((n, 3, 16, 16), 4, seed=int(g["tape_seed"]))
+    with replay(tape, [None] * 4):
+        out, inter = smp.sample(4, n, (3, 16, 16), eta=eta, x_T=x_T.to(cuda_dev), verbose=False,
+                                log_every_t=1)
+    assert rel_l2(out, tt(g["x0"])) <= 5e-3
+    assert rel_l2(inter["pred_x0"][-1], tt(g["pred_x0_last"])) <= 5e-3
