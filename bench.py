@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""Benchmark of the reverse-sampling hot path (BASELINE.json metric: 256x256 cloud-removal
+images/sec at T=1000 DDPM; UNet ms/step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3]
+
+One "step" = one DDPM reverse step of the whole per-GPU batch: UNet forward (eps) + fused
+posterior update + next step's 'sum' conditioning mix.  images/sec = images in flight /
+(T x seconds per step), T = 1000.  Prints ONE JSON line (rank 0).
+
+  value        steps timed on the device with every input resident in HBM
+  e2e          the same step driven through the public drop-in API (EODiffusion methods ->
+               C ABI) from pinned HOST buffers, H2D/D2H copies inside the timed region
+  roofline     the dominant kernel family (tcgen05 implicit-GEMM conv), timed live with CUDA
+               events per op (eo_unet_forward_timed) against MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (port of the reference path) on the host cores, bounded sample
+
+`--impl reference` times the reference's CPU implementation of the path (the oracle port: the
+reference is pure Python/PyTorch and /root/reference is not present on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_DDPM = 1000
+ARCH = dict(in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
+            attention_resolutions=[4, 8], channel_mult=[1, 2, 3, 4], num_heads=8)
+# BASELINE.json configs; c3 (the configuration the metric is quoted on) is the default
+WORKLOADS = {
+    "c1": dict(size=64, batch=1, desc="64x64 batch 1 (reference notebook case)"),
+    "c2": dict(size=128, batch=16, desc="128x128 batch 16"),
+    "c3": dict(size=256, batch=64, desc="256x256 batch 64 per GPU"),
+}
+METRIC = "ddpm_T1000_cloud_removal_images_per_sec"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def randomize_zero_init_(model, seed=4321):
+    """The reference zero-initialises 35 convs, so a fresh UNet outputs 0 and
+    does no representative arithmetic.  Re-draw them and perturb the GroupNorm affines."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.Conv2d)) and not bool(m.weight.any()):
+                fan_in = m.weight[0].numel()
+                bound = 1.0 / math.sqrt(fan_in)
+                m.weight.copy_((torch.rand(m.weight.shape, generator=g) * 2 - 1) * bound)
+                m.bias.copy_((torch.rand(m.bias.shape, generator=g) * 2 - 1) * bound)
+            elif isinstance(m, torch.nn.GroupNorm):
+                m.weight.copy_(1 + 0.1 * torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+    return model
+
+
+def synth_inputs(n, size, seed, device, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    gt = torch.rand((n, 3, size, size), generator=g)
+    mask = (torch.rand((n, 1, size, size), generator=g) > 0.3).float()
+    x = torch.randn((n, 3, size, size), generator=g)
+    nz = [torch.randn((n, 3, size, size), generator=g) for _ in range(2)]
+    host = dict(gt=gt, mask=mask, x=x, nz0=nz[0], nz1=nz[1])
+    if pin:
+        host = {k: v.pin_memory() for k, v in host.items()}
+    dev = {k: v.to(device) for k, v in host.items()}
+    return host, dev
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            log(f"[bench] NVML unavailable: {e}")
+
+    NAMES = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(tflops=float(p["bf16_tflops_sustained"]), gbs=float(p["hbm_gbs"]), src="measured")
+    except Exception:
+        return dict(tflops=1590.0, gbs=6650.0, src="fallback")   # B200_PROFILING.md fallback (burst)
+
+
+# ----------------------------------------------------------------------------------------
+# CPU legs (the oracle port of the reference path): cpu_baseline and --impl reference
+# ----------------------------------------------------------------------------------------
+def cpu_reference_steps(size, batch, steps, warmup):
+    """Time `steps` sampler steps ('sum' mix + UNet + clipped posterior) of the oracle on the host
+    cores.  Returns seconds per step."""
+    from oracle import oracle as O          # test infrastructure: allowed in the CPU legs only
+    from eo_diffusion_b200 import UNetModel
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1234)
+    m = randomize_zero_init_(UNetModel(image_size=size, **ARCH))
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    cfg = O.full_cfg(image_size=size, **ARCH)
+    s = O.cosine_schedule(T_DDPM)
+    host, _ = synth_inputs(batch, size, 0, "cpu")
+    x, gt, mask = host["x"], host["gt"], host["mask"]
+    times = []
+    with torch.no_grad():
+        for k in range(warmup + steps):
+            t0 = time.perf_counter()
+            t = torch.full((batch,), T_DDPM - 1 - k, dtype=torch.long)
+            nz = host["nz0"] if k % 2 == 0 else host["nz1"]
+            x = O.sum_mix(s, x, gt, mask, t, nz)
+            eps = O.unet_forward(sd, cfg, x, t)
+            x = O.reverse_step_clip(s, x, t, nz, eps)
+            if k >= warmup:
+                times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    size = wl["size"]
+    sample_b = 1
+    sec = cpu_reference_steps(size, sample_b, args.steps, args.warmup)
+    val = sample_b / (T_DDPM * sec)
+    cores = torch.get_num_threads()
+    sample = f"{sample_b} image(s) of {size}x{size}, {args.steps} sampler steps (of T={T_DDPM}) after {args.warmup} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}, DDPM T={T_DDPM}, cond 'sum', clipped; "
+                               f"CPU arm runs a bounded sample: {sample}"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import ctypes as C
+    from eo_diffusion_b200 import EODiffusion, UNetModel, _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = _lib.lib()
+    _lib.check(L.eo_device_check(), "eo_device_check")
+
+    size, B, mode = wl["size"], args.batch or wl["batch"], args.mode
+    torch.manual_seed(1234)
+    model = randomize_zero_init_(UNetModel(image_size=size, **ARCH)).to(dev).set_compute_mode(mode)
+    diff = EODiffusion(model, size, 3, timesteps=T_DDPM, cond_type="sum").to(dev)
+    host, d = synth_inputs(B, size, 100 + rank, dev, pin=True)
+    tab = diff._coef_table(dev)
+    ts_rows = diff._timestep_rows(B, dev)
+    hw = size * size
+    nz = [d["nz0"], d["nz1"]]
+    x = d["x"].clone()
+    stream = _lib.stream_ptr
+
+    def device_step(k):
+        i = T_DDPM - 1 - (k % (T_DDPM - 1))           # i >= 1
+        pred = model(x, ts_rows[i])
+        _lib.check(L.eo_ddpm_step_mix(_lib.ptr(x), _lib.ptr(pred), _lib.ptr(nz[k % 2]), _lib.ptr(ts_rows[i]),
+                                      _lib.ptr(d["gt"]), _lib.ptr(d["mask"]), _lib.ptr(nz[(k + 1) % 2]),
+                                      _lib.ptr(ts_rows[i - 1]), _lib.ptr(tab), _lib.ptr(x), B, 3, hw, 1, 1,
+                                      stream()), "eo_ddpm_step_mix")
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident steps ------------------------------------------------------------
+    _lib.check(L.eo_ddpm_sum_mix(_lib.ptr(x), _lib.ptr(d["gt"]), _lib.ptr(d["mask"]), _lib.ptr(nz[0]),
+                                 _lib.ptr(ts_rows[T_DDPM - 1]), _lib.ptr(tab), _lib.ptr(x), B, 3, hw, stream()))
+    for k in range(args.warmup):
+        device_step(k)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        device_step(args.warmup + k)
+    e1.record()
+    barrier()
+    clk = clocks.finish()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    value = world * B / (T_DDPM * ms_step * 1e-3)
+    assert bool(torch.isfinite(x).all()), "sampler state diverged"
+    launches_step = model.launches_per_forward() + 1
+
+    # ---- end to end through the public API from pinned host buffers ---------------------------
+    hx = host["x"].clone().pin_memory()
+    out_host = torch.empty_like(hx).pin_memory()
+    dx, dn, dgt, dm = (torch.empty_like(d["x"]), torch.empty_like(d["x"]), torch.empty_like(d["gt"]),
+                       torch.empty_like(d["mask"]))
+    h2d = sum(t.numel() * 4 for t in (hx, host["nz0"], host["gt"], host["mask"]))
+    d2h = out_host.numel() * 4
+
+    def e2e_step(k):
+        i = T_DDPM - 1 - (k % (T_DDPM - 1))
+        dx.copy_(hx, non_blocking=True)
+        dn.copy_(host["nz0"] if k % 2 == 0 else host["nz1"], non_blocking=True)
+        dgt.copy_(host["gt"], non_blocking=True)
+        dm.copy_(host["mask"], non_blocking=True)
+        t = ts_rows[i]
+        _lib.check(L.eo_ddpm_sum_mix(_lib.ptr(dx), _lib.ptr(dgt), _lib.ptr(dm), _lib.ptr(dn), _lib.ptr(t),
+                                     _lib.ptr(tab), _lib.ptr(dx), B, 3, hw, stream()))
+        nxt = diff._reverse_diffusion_with_clip(dx, t, dn)      # public method: UNet + posterior
+        out_host.copy_(nxt, non_blocking=True)
+
+    n_e2e = max(2, min(args.steps, 5))
+    e2e_step(0)
+    barrier()
+    e0.record()
+    for k in range(n_e2e):
+        e2e_step(k + 1)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / n_e2e)
+    e2e_value = world * B / (T_DDPM * ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel family, timed per op with CUDA events --------------
+    roofline = None
+    breakdown = {}
+    if rank == 0:
+        h = C.c_void_p(model._handle)
+        nops = L.eo_unet_num_ops(h)
+        ms = (C.c_float * nops)()
+        eps = torch.empty((B, 3, size, size), device=dev)
+        for _ in range(2):   # second pass is the warm one
+            _lib.check(L.eo_unet_forward_timed(h, _lib.ptr(x), 3, None, 0, _lib.ptr(ts_rows[500]), None,
+                                               _lib.ptr(eps), B, stream(), ms), "eo_unet_forward_timed")
+        name, kern, fl, by = C.c_char_p(), C.c_char_p(), C.c_double(), C.c_double()
+        for i in range(nops):
+            L.eo_unet_op_info(h, i, C.byref(name), C.byref(kern), C.byref(fl), C.byref(by))
+            e = breakdown.setdefault(kern.value.decode(), dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            e["ms"] += ms[i]
+            e["flops"] += fl.value * B
+            e["bytes"] += by.value * B
+            e["launches"] += 1
+        peaks = measured_peaks()
+        fam = "k_conv_tc" if "k_conv_tc" in breakdown else "k_conv_simt"
+        e = breakdown[fam]
+        ach = e["flops"] / (e["ms"] * 1e-3) / 1e12
+        total_ms = sum(v["ms"] for v in breakdown.values())
+        roofline = {"bound": "tensor", "kernel": fam, "achieved": ach, "peak": peaks["tflops"],
+                    "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None,
+                    "peak_source": f"{peaks['src']} bf16_tflops_sustained",
+                    "flops_per_launch_avg": e["flops"] / e["launches"], "launches_per_step": e["launches"],
+                    "share_of_unet_time": e["ms"] / total_ms}
+        log("[bench] per-kernel-family breakdown of one UNet forward (CUDA events per op):")
+        for kname, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"]):
+            extra = ""
+            if v["flops"]:
+                extra = f"{v['flops'] / (v['ms'] * 1e-3) / 1e12:8.1f} TFLOP/s"
+            elif v["bytes"]:
+                extra = f"{v['bytes'] / (v['ms'] * 1e-3) / 1e9:8.1f} GB/s"
+            log(f"    {kname:18s} {v['ms']:9.3f} ms  {100 * v['ms'] / total_ms:5.1f}%  x{v['launches']:3d}  {extra}")
+        if args.breakdown:
+            ops = []
+            for i in range(nops):
+                L.eo_unet_op_info(h, i, C.byref(name), C.byref(kern), C.byref(fl), C.byref(by))
+                ops.append(dict(name=name.value.decode(), kernel=kern.value.decode(), ms=ms[i],
+                                flops=fl.value * B, bytes=by.value * B))
+            with open(args.breakdown, "w") as f:
+                json.dump(dict(workload=args.workload, batch=B, size=size, mode=mode, ops=ops), f, indent=1)
+
+    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample_b, sample_steps = 1, 2
+        sec = cpu_reference_steps(size, sample_b, sample_steps, 1)
+        cpu = {"value": sample_b / (T_DDPM * sec), "unit": "images/s", "cores": torch.get_num_threads(),
+               "kind": "port", "ms_per_step": sec * 1e3,
+               "sample": f"{sample_b} image of {size}x{size}, {sample_steps} sampler steps after 1 warm-up "
+                         f"(oracle port of the reference CPU path, fp32)"}
+
+    if world > 1:
+        # the one collective of the path: gather the final images of all ranks
+        import torch.distributed as dist
+        gathered = torch.empty((world * B, 3, size, size), device=dev)
+        dist.all_gather_into_tensor(gathered, x)
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+
+    if rank == 0:
+        flops_img = sum(v["flops"] for v in breakdown.values()) / B if breakdown else None
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": mode, "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}, DDPM T={T_DDPM}, cond 'sum' (3+3->3 ch), "
+                                   "clipped posterior, UNet base 128 mult [1,2,3,4] attn [4,8] 2 res blocks 8 heads",
+                       "batch_per_gpu": B, "image": size, "parallelism": f"batch-sharded x{world}",
+                       "l2": "activations per step (GBs) exceed the 126 MB L2; no flush needed"
+                             if B * size * size * 128 * 2 > 4 * 126e6 else
+                             "working set fits L2: numbers are L2-warm"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e, "steps": n_e2e},
+            "gpu_launches": launches_step * args.steps,
+            "clocks": clk,
+            "roofline": roofline,
+            "unet_algorithmic_gflop_per_image_step": flops_img / 1e9 if flops_img else None,
+            "cpu_baseline": cpu,
+        }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--breakdown", default="", help="write the per-op timing JSON here")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3                    # timing rule: at least 3 warm-up steps
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

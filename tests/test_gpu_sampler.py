@@ -57,8 +57,9 @@ def test_sum_mix_and_steps_bit_exact(cuda_dev, shape):
         # fused step + next iteration's mix
         if tval > 0:
             t2 = t - 1
+            dt2 = d(t2)
             _lib.check(L.eo_ddpm_step_mix(_lib.ptr(dx), _lib.ptr(de), _lib.ptr(dn), _lib.ptr(dt), _lib.ptr(dg),
-                                          _lib.ptr(dm), _lib.ptr(dn2), _lib.ptr(d(t2)), _lib.ptr(tab),
+                                          _lib.ptr(dm), _lib.ptr(dn2), _lib.ptr(dt2), _lib.ptr(tab),
                                           _lib.ptr(out), n, c, h * w, 1, 1, st))
             want = O.sum_mix(s, O.reverse_step_clip(s, x, t, nz, eps), gt, mask, t2, nz2)
             assert torch.equal(out.cpu(), want), f"step_mix t={tval}"
@@ -73,9 +74,9 @@ def test_mixed_timesteps_per_sample(cuda_dev):
     x, eps, nz = (torch.randn(shape, generator=g) for _ in range(3))
     t = torch.tensor([999, 3, 512, 1])
     out = torch.empty(shape, device=cuda_dev)
-    _lib.check(L.eo_ddpm_step(_lib.ptr(x.to(cuda_dev)), _lib.ptr(eps.to(cuda_dev)), _lib.ptr(nz.to(cuda_dev)),
-                              _lib.ptr(t.to(cuda_dev)), _lib.ptr(tab), _lib.ptr(out), 4, 3, 64, 1, 1,
-                              _lib.stream_ptr()))
+    dx, de, dn, dt = x.to(cuda_dev), eps.to(cuda_dev), nz.to(cuda_dev), t.to(cuda_dev)   # keep alive
+    _lib.check(L.eo_ddpm_step(_lib.ptr(dx), _lib.ptr(de), _lib.ptr(dn), _lib.ptr(dt), _lib.ptr(tab),
+                              _lib.ptr(out), 4, 3, 64, 1, 1, _lib.stream_ptr()))
     assert torch.equal(out.cpu(), O.reverse_step_clip(s, x, t, nz, eps))
 
 
@@ -133,8 +134,8 @@ def test_cfg_combine_and_forward_diffusion(cuda_dev):
     g = torch.Generator().manual_seed(9)
     a, b = torch.randn(2, 3, 9, 9, generator=g), torch.randn(2, 3, 9, 9, generator=g)
     out = torch.empty_like(a, device=cuda_dev)
-    _lib.check(L.eo_cfg_combine(_lib.ptr(a.to(cuda_dev)), _lib.ptr(b.to(cuda_dev)), 2.5, _lib.ptr(out),
-                                a.numel(), _lib.stream_ptr()))
+    da, db = a.to(cuda_dev), b.to(cuda_dev)
+    _lib.check(L.eo_cfg_combine(_lib.ptr(da), _lib.ptr(db), 2.5, _lib.ptr(out), a.numel(), _lib.stream_ptr()))
     assert torch.equal(out.cpu(), a + 2.5 * (b - a))
     d = EODiffusion(Stub(), 9, 3, timesteps=1000).to(cuda_dev)
     t = torch.tensor([10, 900])

@@ -40,6 +40,7 @@ def test_eps_fp32_mode(cuda_dev, name):
     eps = m(tt(g["x"]).to(cuda_dev), tt(g["t"]).to(cuda_dev), cond=cond)
     assert eps.shape == g["eps"].shape and eps.dtype == torch.float32
     err = rel_l2(eps, tt(g["eps"]))
+    print(f"[parity] fp32 {name}: eps rel L2 {err:.3e}")
     assert err <= TOL["fp32"], f"{name}: rel L2 {err:.3e}"
 
 
@@ -51,6 +52,7 @@ def test_eps_bf16_mode(cuda_dev, name):
     cond = tt(g["cond"]).to(cuda_dev) if "cond" in g else None
     eps = m(tt(g["x"]).to(cuda_dev), tt(g["t"]).to(cuda_dev), cond=cond)
     err = rel_l2(eps, tt(g["eps"]))
+    print(f"[parity] bf16 {name}: eps rel L2 {err:.3e}")
     assert err <= TOL["bf16"], f"{name}: rel L2 {err:.3e}"
 
 
@@ -157,6 +159,8 @@ def test_base64_ddpm_sum_trajectory(cuda_dev, tmp_path, mode, mae_tol):
     assert torch.equal(rec[0][1].cpu(), tt(g["xt_step0"]))
     assert rel_l2(rec[0][2], tt(g["eps_step0"])) <= TOL[mode]
     mae = float((out.cpu() - tt(g["x0"])).abs().mean())
+    print(f"[parity] {mode} base64 T20 trajectory: mean-abs {mae:.3e}, step-0 eps rel L2 "
+          f"{rel_l2(rec[0][2], tt(g['eps_step0'])):.3e}, step-19 eps rel L2 {rel_l2(rec[19][2], tt(g['eps_step19'])):.3e}")
     assert mae <= mae_tol, mae
 
 
