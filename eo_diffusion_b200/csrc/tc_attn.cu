@@ -12,12 +12,13 @@
 // core, so that one tile's softmax (the MUFU-bound part: 128 exp2 per row per block against
 // 512 tensor cycles) overlaps the other tile's MMAs:
 //   S_t,j = Q_t K_j^T        tcgen05.mma  M=128 N=128 K=64   -> TMEM S_t
-//   P_t,j = exp2(S_t,j - m)  128 softmax threads per tile, one query row each; ONE pass over
-//                            TMEM in 32-column chunks using a lazily updated reference
-//                            maximum m (rescale only when a logit exceeds m by 2^8);
-//                            written as bf16 into a 128B-swizzled K-major smem tile
-//   O_t,j = P_t,j V_j        tcgen05.mma  M=128 N=64 K=128, V consumed MN-major straight from
-//                            the [key][d] TMA tile -> TMEM O_t, folded into registers
+//   P_t,j = exp2(S_t,j - m)  128 softmax threads per tile, one query row each: the whole 128-logit
+//                            row is pulled into registers with one batch of tcgen05.ld, m is a
+//                            lazily updated reference maximum (O and l are rescaled only when a
+//                            logit exceeds m by 2^8); P is written as bf16 into a 128B-swizzled
+//                            K-major smem tile
+//   O_t  += P_t,j V_j        tcgen05.mma  M=128 N=64 K=128, V consumed MN-major straight from
+//                            the [key][d] TMA tile; O_t accumulates in TMEM across all blocks
 // Warp roles (320 threads): warp 0 TMA loader, warp 1 TMEM owner + MMA issuer, warps 2..5
 // softmax of tile 0, warps 6..9 softmax of tile 1.  All hand-offs are mbarriers.
 //
@@ -52,67 +53,21 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// One 128-key block of one query row: P = exp2(S*scale - m) as bf16 into the swizzled smem row,
-// rs = row sum.  m is the lazily updated reference maximum: when some row of the warp sees a
-// logit above m + 2^8 the warp takes the exact row maximum as the new reference (alpha carries
-// the rescale factor of everything accumulated so far) and redoes the block.  All TMEM loads
-// are warp-collective, so every decision here is warp-uniform.
-template <bool MASKED>
-__device__ __forceinline__ void softmax_block(uint32_t s_addr, uint8_t* prow, int row, int nvalid,
-                                              float scale_log2, float& m, float& alpha, float& rs) {
-  bool redo = true;
-  while (redo) {
-    redo = false;
-    rs = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < KT; c += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(s_addr + c, v);
-      tc::tmem_ld_wait();
-      if (MASKED) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i >= nvalid) v[i] = 0xff800000u;   // -inf
-      }
-      float cm = __uint_as_float(v[0]);
-#pragma unroll
-      for (int i = 1; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
-      if (__any_sync(0xffffffffu, cm * scale_log2 > m + RESCALE_THRESHOLD)) {
-        float full = -INFINITY;
-#pragma unroll 1
-        for (int c2 = 0; c2 < KT; c2 += 32) {
-          uint32_t w[32];
-          tc::tmem_ld_32x32(s_addr + c2, w);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (!MASKED || c2 + i < nvalid) full = fmaxf(full, __uint_as_float(w[i]));
-        }
-        const float m_new = fmaxf(m, full * scale_log2);
-        alpha *= ex2(m - m_new);          // first block: ex2(-inf) = 0
-        m = m_new;
-        redo = true;
-        break;
-      }
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m));
-        const float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m));
-        rs += p0 + p1;
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
-      }
-      // 32 keys = 64 B = four 16 B pieces; piece index within the 128 B row: (c%64)/8 + jj
-      uint8_t* half = prow + (c >> 6) * TILE_BYTES;
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int piece = ((c & 63) >> 3) + jj;
-        uint4 w4 = make_uint4(pk[jj * 4], pk[jj * 4 + 1], pk[jj * 4 + 2], pk[jj * 4 + 3]);
-        *reinterpret_cast<uint4*>(half + ((piece ^ (row & 7)) << 4)) = w4;
-      }
-    }
-  }
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+         "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
+         "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+         "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+         "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(320, 1)
@@ -180,7 +135,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict
                           idesc_s, k != 0 ? 1u : 0u);
         tc::umma_commit(&s_full[t]);
       };
-      // O_t,j = P_t,j V_j into TMEM O_t (overwrite; the softmax threads fold it into registers)
+      // O_t (+)= P_t,j V_j in TMEM; the softmax threads rescale O_t in place when m moves
       auto issue_pv = [&](int t, int j) {
         const int s = j % KV_STAGES;
         const uint64_t vdesc = tc::make_sw128_desc(tc::smem_u32(smem + OFF_V + s * TILE_BYTES));
@@ -191,7 +146,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict
           // A: P tile, half k/4 (64 keys = one 128 B row segment), 32 B per 16 keys
           const uint64_t pdesc = tc::make_sw128_desc(pbase + (k >> 2) * TILE_BYTES + (k & 3) * 32);
           // B: V tile [key][d], 16 keys = 16 rows of 128 B
-          tc::umma_f16_ss(d, pdesc, tc::desc_advance(vdesc, k * 16 * 128), idesc_o, k != 0 ? 1u : 0u);
+          tc::umma_f16_ss(d, pdesc, tc::desc_advance(vdesc, k * 16 * 128), idesc_o, (j | k) != 0 ? 1u : 0u);
         }
         tc::umma_commit(&o_full[t]);
       };
@@ -206,11 +161,13 @@ k_attn_tc(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict
           tc::tc_fence_after();
         }
         for (int t = 0; t < ntiles; ++t) {
+          // p_full: P_t,j is in smem AND S_t has been consumed -> the next S first (the softmax
+          // of block j+1 waits on it), then this block's PV
           tc::mbar_wait(&p_full[t], j & 1);
           tc::tc_fence_after();
+          if (more) issue_s(t, j + 1);
           issue_pv(t, j);
           if (t == ntiles - 1) tc::umma_commit(&kv_empty[j % KV_STAGES]);   // K_j, V_j consumed
-          if (more) issue_s(t, j + 1);
         }
       }
     }
@@ -223,45 +180,100 @@ k_attn_tc(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict
     const uint32_t s_addr = tmem + lane_addr + (t ? TM_S1 : TM_S0);
     const uint32_t o_addr = tmem + lane_addr + (t ? TM_O1 : TM_O0);
     uint8_t* prow = smem + OFF_P + t * 2 * TILE_BYTES + row * 128;
-    float acc[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-    float m = -INFINITY, l = 0.f;       // m: reference maximum (log2 domain) of everything folded so far
+    float m = -INFINITY, l = 0.f;       // m: reference maximum (log2 domain) of everything accumulated so far
     const int last_valid = T - (nblk - 1) * KT;   // valid keys in the last block
 
     for (int j = 0; j < nblk; ++j) {
       tc::mbar_wait(&s_full[t], j & 1);
       tc::tc_fence_after();
-      if (j > 0) {
-        // S_t,j is issued after PV_t,j-1, so O_t,j-1 is complete: fold it (scale of m as of block j-1)
-        tc::mbar_wait(&o_full[t], (j - 1) & 1);
-        tc::tc_fence_after();
+      const int nvalid = (j == nblk - 1) ? last_valid : KT;   // < KT only in a ragged last block
+      // ---- pass 1: row maximum.  32-column chunks, the next chunk's tcgen05.ld in flight while
+      // this one is reduced (two register buffers; wait::ld covers the single outstanding load)
+      uint32_t va[32], vb[32];
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      tc::tmem_ld_32x32(s_addr, va);
+      tc::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < HD; c += 32) {
-          uint32_t v[32];
-          tc::tmem_ld_32x32(o_addr + c, v);
-          tc::tmem_ld_wait();
+      for (int c = 0; c < KT; c += 32) {
+        uint32_t* cur = (c & 32) ? vb : va;
+        uint32_t* nxt = (c & 32) ? va : vb;
+        if (c + 32 < KT) tc::tmem_ld_32x32(s_addr + c + 32, nxt);
+        if (nvalid < KT) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c + i] += __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i)
+            if (c + i >= nvalid) cur[i] = 0xff800000u;   // -inf
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mx[k] = max3(mx[k], __uint_as_float(cur[i + 2 * k]), __uint_as_float(cur[i + 2 * k + 1]));
+        tc::tmem_ld_wait();
+      }
+      const float cm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2;
+      // warp-uniform decision (the TMEM accesses below are warp-collective)
+      if (__any_sync(0xffffffffu, cm > m + RESCALE_THRESHOLD)) {
+        const float m_new = fmaxf(m, cm);
+        const float alpha = ex2(m - m_new);          // first block: ex2(-inf) = 0
+        m = m_new;
+        l *= alpha;
+        if (j > 0) {
+          // O_t holds blocks < j (PV_t,j-1 has completed: o_full); rescale it in place
+          tc::mbar_wait(&o_full[t], (j - 1) & 1);
+          tc::tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < HD; c += 32) {
+            uint32_t o[32];
+            tc::tmem_ld_32x32(o_addr + c, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(o_addr + c, o);
+          }
+          tmem_st_wait();
         }
       }
-      float alpha = 1.f, rs = 0.f;
-      if (j == nblk - 1 && last_valid < KT)
-        softmax_block<true>(s_addr, prow, row, last_valid, scale_log2, m, alpha, rs);
-      else
-        softmax_block<false>(s_addr, prow, row, KT, scale_log2, m, alpha, rs);
-      // hand P_t,j (and the consumed S_t) to the MMA warp
+      // P smem is free once PV_t,j-1 has read it (issued a whole softmax ago: no real wait)
+      if (j > 0) tc::mbar_wait(&o_full[t], (j - 1) & 1);
+      // ---- pass 2: P = exp2(S*scale - m) -> bf16 -> swizzled smem; row sum
+      float rs0 = 0.f, rs1 = 0.f;
+      tc::tmem_ld_32x32(s_addr, va);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < KT; c += 32) {
+        uint32_t* cur = (c & 32) ? vb : va;
+        uint32_t* nxt = (c & 32) ? va : vb;
+        if (c + 32 < KT) tc::tmem_ld_32x32(s_addr + c + 32, nxt);
+        if (nvalid < KT) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i >= nvalid) cur[i] = 0xff800000u;
+        }
+        // 32 keys = 64 B = four 16 B pieces of the 128 B row of the 64-key half c/64, XOR-swizzled
+        uint8_t* half = prow + (c >> 6) * TILE_BYTES;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = jj * 8 + 2 * e;
+            const float p0 = ex2(fmaf(__uint_as_float(cur[i]), scale_log2, -m));
+            const float p1 = ex2(fmaf(__uint_as_float(cur[i + 1]), scale_log2, -m));
+            rs0 += p0; rs1 += p1;
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          const int piece = ((c & 63) >> 3) + jj;
+          *reinterpret_cast<uint4*>(half + ((piece ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        tc::tmem_ld_wait();
+      }
+      // hand P_t,j (and the consumed S_t, and the possibly rescaled O_t) to the MMA warp
       tc::fence_proxy_async_smem();
       tc::tc_fence_before();
       tc::mbar_arrive(&p_full[t]);
-      if (alpha != 1.f) {
-#pragma unroll
-        for (int d = 0; d < HD; ++d) acc[d] *= alpha;
-        l *= alpha;
-      }
-      l += rs;
+      l += rs0 + rs1;
     }
-    // last block's PV
     tc::mbar_wait(&o_full[t], (nblk - 1) & 1);
     tc::tc_fence_after();
     const int qi = q0 + t * QT + row;
@@ -269,8 +281,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict
     __nv_bfloat16* op = out + ((long long)b * T + qi) * (heads * ch) + h * ch;
 #pragma unroll
     for (int c = 0; c < HD; c += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(o_addr + c, v);
+      uint32_t o[32];
+      tc::tmem_ld_32x32(o_addr + c, o);
       tc::tmem_ld_wait();
       if (qi < T) {
 #pragma unroll
@@ -280,8 +292,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w4);
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              h2[e] = __floats2bfloat162_rn((acc[c + d + 2 * e] + __uint_as_float(v[d + 2 * e])) * inv,
-                                            (acc[c + d + 2 * e + 1] + __uint_as_float(v[d + 2 * e + 1])) * inv);
+              h2[e] = __floats2bfloat162_rn(__uint_as_float(o[d + 2 * e]) * inv,
+                                            __uint_as_float(o[d + 2 * e + 1]) * inv);
             *reinterpret_cast<uint4*>(op + c + d) = w4;
           }
         }
