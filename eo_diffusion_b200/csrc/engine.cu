@@ -793,25 +793,28 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
     const int odt = act_dt;
     // the packed K order is (tap, channel); with two sources the kernel needs per-source
     // segments, so a second packing ordered (x taps, cond taps) is built lazily per split
+    const bool stem_kernel = (size_t)9 * cin * 64 * sizeof(float) <= 200 * 1024;
     push("input_blocks.0", [=](int B, cudaStream_t s) -> int {
+      const float* Wuse = Wp;
+      if (io_cc != 0) {
+        Wuse = stem_split_weights(io_cx, io_cc, s);
+        if (!Wuse) return EO_ERR_CUDA;
+      }
+      if (stem_kernel)
+        return launch_conv_stem(io_x, io_cx, io_cond, io_cc, Wuse, bias, ptr(h.off), odt, B, H, W, cout, s);
       ConvSimtParams p;
       p.B = B; p.Hin = H; p.Win = W; p.Hout = H; p.Wout = W; p.stride = 1; p.up = 0;
       p.Cout = cout; p.bias = bias; p.out = ptr(h.off); p.out_dt = odt;
-      if (io_cc == 0) {
-        p.nsrc = 1;
-        p.src[0].ptr = io_x; p.src[0].C = cin; p.src[0].ksize = 3; p.src[0].dt = DT_F32; p.src[0].nchw = 1; p.src[0].w_off = 0;
-        p.W = Wp; p.Ktot = K;
-      } else {
-        float* Wsplit = stem_split_weights(io_cx, io_cc, s);
-        if (!Wsplit) return EO_ERR_CUDA;
-        p.nsrc = 2;
-        p.src[0].ptr = io_x; p.src[0].C = io_cx; p.src[0].ksize = 3; p.src[0].dt = DT_F32; p.src[0].nchw = 1; p.src[0].w_off = 0;
+      p.W = Wuse; p.Ktot = K;
+      p.nsrc = io_cc == 0 ? 1 : 2;
+      p.src[0].ptr = io_x; p.src[0].C = io_cx; p.src[0].ksize = 3; p.src[0].dt = DT_F32; p.src[0].nchw = 1; p.src[0].w_off = 0;
+      if (io_cc != 0) {
         p.src[1].ptr = io_cond; p.src[1].C = io_cc; p.src[1].ksize = 3; p.src[1].dt = DT_F32; p.src[1].nchw = 1; p.src[1].w_off = 9 * io_cx;
-        p.W = Wsplit; p.Ktot = K;
       }
       return launch_conv_simt(p, s);
     });
-    note("k_conv_simt", 2.0 * H * W * cout * K, 0);
+    (void)cin;
+    note(stem_kernel ? "k_conv_stem" : "k_conv_simt", 2.0 * H * W * cout * K, 0);
   }
   named[in_blocks[0].name] = h;
 
@@ -842,14 +845,16 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
     float* Wp = nullptr; int K = 0;
     if ((rc = pack_simt({{w("out.2.weight"), final_ch, 3, 0, final_ch}}, cfg.out_channels, &Wp, &K, st))) return rc;
     const float* bias = w("out.2.bias");
-    Act hh = h;
     const int cout = cfg.out_channels, C = final_ch;
     const int adt = act_dt;
-    const bool small = (mode == EO_MODE_BF16) && cout <= 16 && (size_t)(9 * C * cout + 2 * C) * 4 <= 200 * 1024;
+    const bool small = (mode == EO_MODE_BF16) && cout <= 16 && (size_t)(9 * C * (cout <= 4 ? 4 : 16) + 2 * C) * 4 <= 200 * 1024;
+    // bf16 mode: GroupNorm + SiLU applied once per element by the bandwidth pass (the conv would
+    // otherwise redo it for each of its 9 taps), then a plain small-N conv
+    Act hh = small ? plan_gn_apply("out.0", h, nullptr, g, 1) : h;
     push("out", [=](int B, cudaStream_t s) -> int {
       if (small) {
         ConvSmallNParams p;
-        p.x = ptr(hh.off); p.dt = DT_BF16; p.gn_scale = ptr<float>(g.scale_off); p.gn_shift = ptr<float>(g.shift_off);
+        p.x = ptr(hh.off); p.dt = DT_BF16; p.gn_scale = nullptr; p.gn_shift = nullptr;
         p.B = B; p.H = H; p.W = W; p.C = C; p.Cout = cout; p.Wp = Wp; p.bias = bias; p.out_nchw = io_out;
         return launch_conv_small_n(p, s);
       }

@@ -45,6 +45,11 @@ struct ConvSimtParams {
 };
 int launch_conv_simt(const ConvSimtParams& p, cudaStream_t st);
 
+// stem conv: conv3x3 over cat(x, cond), both NCHW fp32 with few channels; Wp packed [K][Cout] fp32
+// with K ordered (x: tap, c), (cond: tap, c); NHWC output of dtype out_dt
+int launch_conv_stem(const float* x, int Cx, const float* cond, int Cc, const float* Wp, const float* bias,
+                     void* out, int out_dt, int B, int H, int W, int Cout, cudaStream_t st);
+
 // out conv of the bf16 mode: GN+SiLU folded on load, tiny Cout (<=16), NHWC in (any dtype),
 // NCHW fp32 out.  Bandwidth kernel (arithmetic intensity ~26 flop/B).
 struct ConvSmallNParams {

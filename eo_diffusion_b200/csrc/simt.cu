@@ -17,16 +17,22 @@ namespace eo {
 //   the epilogue.
 // =======================================================================================
 namespace {
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BK = 16;
 
 __device__ __forceinline__ float load_elem(const ConvSrc& s, long long idx) {
   if (s.dt == DT_F32) return reinterpret_cast<const float*>(s.ptr)[idx];
   return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s.ptr)[idx]);
 }
 
+// BM x BN output tile per CTA (256 threads as 16 x 16, TM x TN outputs each), K in steps of 16.
+// <64,64>: small layers / narrow outputs; <128,128>: 64 FFMA per 4 LDS.128 for the big ones.
+template <int BM, int BN>
 __global__ void __launch_bounds__(256) k_conv_simt(const ConvSimtParams p) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  constexpr int TM = BM / 16, TN = BN / 16;
+  constexpr int AK = BM * BK / 256;      // k values of one pixel loaded per thread (4 or 8)
+  constexpr int TPP = BK / AK;           // threads per pixel
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const long long M = (long long)p.B * p.Hout * p.Wout;
@@ -34,7 +40,7 @@ __global__ void __launch_bounds__(256) k_conv_simt(const ConvSimtParams p) {
   const int n0 = blockIdx.y * BN;
 
   // operand-load roles
-  const int lm = tid >> 2, kq = (tid & 3) * 4;
+  const int lm = tid / TPP, kq = (tid % TPP) * AK;
   const long long gm = m0 + lm;
   int pb = 0, poh = 0, pow_ = 0;
   const bool m_ok = gm < M;
@@ -44,13 +50,13 @@ __global__ void __launch_bounds__(256) k_conv_simt(const ConvSimtParams p) {
     poh = r / p.Wout;
     pow_ = r - poh * p.Wout;
   }
-  const int kr = tid >> 4, nc = (tid & 15) * 4;
+  const int kr = tid >> 4, nc = (tid & 15) * TN;
 
-  float acc[4][4];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   for (int s = 0; s < p.nsrc; ++s) {
     const ConvSrc& src = p.src[s];
@@ -58,13 +64,15 @@ __global__ void __launch_bounds__(256) k_conv_simt(const ConvSimtParams p) {
     const int KK = src.ksize * src.ksize * C;
     const bool uniform = (C % BK) == 0;
     for (int k0 = 0; k0 < KK; k0 += BK) {
-      // ---- A tile: 64 pixels x 16 k -------------------------------------------------
-      float av[4] = {0.f, 0.f, 0.f, 0.f};
+      // ---- A tile: BM pixels x 16 k -------------------------------------------------
+      float av[AK];
+#pragma unroll
+      for (int j = 0; j < AK; ++j) av[j] = 0.f;
       if (m_ok) {
         int tap_u = 0, c_u = 0;
         if (uniform) { tap_u = k0 / C; c_u = k0 - tap_u * C + kq; }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < AK; ++j) {
           int k = k0 + kq + j;
           if (k >= KK) continue;
           int tap, c;
@@ -97,12 +105,12 @@ __global__ void __launch_bounds__(256) k_conv_simt(const ConvSimtParams p) {
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) As[kq + j][lm] = av[j];
-      // ---- B tile: 16 k x 64 n --------------------------------------------------------
+      for (int j = 0; j < AK; ++j) As[kq + j][lm] = av[j];
+      // ---- B tile: 16 k x BN n --------------------------------------------------------
       {
         int k = k0 + kr;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < TN; ++j) {
           int n = n0 + nc + j;
           Bs[kr][nc + j] = (k < KK && n < p.Cout)
               ? __ldg(p.W + (long long)(src.w_off + k) * p.Cout + n) : 0.f;
@@ -111,30 +119,74 @@ __global__ void __launch_bounds__(256) k_conv_simt(const ConvSimtParams p) {
       __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < BK; ++kk) {
-        float a[4], b[4];
+        float a[TM], b[TN];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+        for (int i = 0; i < TM; i += 4)
+          *reinterpret_cast<float4*>(&a[i]) = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+        for (int j = 0; j < TN; j += 4)
+          *reinterpret_cast<float4*>(&b[j]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN + j]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
       }
       __syncthreads();
     }
   }
 
   // ---- epilogue -----------------------------------------------------------------------
+  const bool vec = !p.out_nchw && (p.Cout % TN) == 0;     // TN contiguous channels per pixel: vector stores
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    long long m = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    long long m = m0 + ty * TM + i;
     if (m >= M) continue;
     int b = (int)(m / ((long long)p.Hout * p.Wout));
     int r = (int)(m - (long long)b * p.Hout * p.Wout);
+    const int nb = n0 + tx * TN;
+    if (vec) {
+      if (nb >= p.Cout) continue;
+      float v[TN];
+      const long long o = m * p.Cout + nb;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int n = n0 + tx * 4 + j;
+      for (int j = 0; j < TN; ++j) {
+        v[j] = acc[i][j];
+        if (p.bias) v[j] += p.bias[nb + j];
+        if (p.bias_nc) v[j] += p.bias_nc[(long long)b * p.ld_bias_nc + nb + j];
+      }
+      if (p.out_dt == DT_F32) {
+        if (p.residual) {
+#pragma unroll
+          for (int j = 0; j < TN; j += 4) {
+            const float4 r4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + o + j);
+            v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < TN; j += 4)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        if (p.residual) {
+#pragma unroll
+          for (int j = 0; j < TN; j += 2) {
+            const float2 r2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
+                reinterpret_cast<const __nv_bfloat16*>(p.residual) + o + j));
+            v[j] += r2.x; v[j + 1] += r2.y;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+          uint2 q;
+          *reinterpret_cast<__nv_bfloat162*>(&q.x) = __floats2bfloat162_rn(v[j], v[j + 1]);
+          *reinterpret_cast<__nv_bfloat162*>(&q.y) = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o + j) = q;
+        }
+      }
+      continue;
+    }
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = nb + j;
       if (n >= p.Cout) continue;
       float v = acc[i][j];
       if (p.bias) v += p.bias[n];
@@ -165,8 +217,112 @@ int launch_conv_simt(const ConvSimtParams& p, cudaStream_t st) {
                EO_ERR_ARG, "conv_simt: 1x1 source with stride/up");
   }
   long long M = (long long)p.B * p.Hout * p.Wout;
-  dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(p.Cout, BN));
-  k_conv_simt<<<grid, 256, 0, st>>>(p);
+  const bool big = p.Cout > 64 && ceil_div(M, 128) * ceil_div(p.Cout, 128) >= num_sms();
+  if (big) {
+    dim3 grid((unsigned)ceil_div(M, 128), (unsigned)ceil_div(p.Cout, 128));
+    k_conv_simt<128, 128><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((unsigned)ceil_div(M, 64), (unsigned)ceil_div(p.Cout, 64));
+    k_conv_simt<64, 64><<<grid, 256, 0, st>>>(p);
+  }
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+
+// =======================================================================================
+// stem conv: conv3x3 over cat(x, cond) given as NCHW fp32 (the reference's input layout), few
+// input channels (K = 9*Cin = 27 ... 252), NHWC output.  reference: input_blocks[0]
+// (unet_openai.py:608) and th.cat([x, cond], 1) (:754-756).
+// One thread = one pixel x 64 output channels: inputs come straight from global memory
+// (coalesced along W), the K x 64 weight slice is broadcast from shared memory (LDS.128).
+// =======================================================================================
+namespace {
+template <typename OutT>
+__global__ void __launch_bounds__(128) k_conv_stem(const float* __restrict__ x, int Cx,
+                                                   const float* __restrict__ cond, int Cc,
+                                                   const float* __restrict__ Wp, const float* __restrict__ bias,
+                                                   OutT* __restrict__ out, int B, int H, int W, int Cout) {
+  extern __shared__ __align__(16) float wsm[];     // [K][64]
+  const int K = 9 * (Cx + Cc);
+  const int n0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < K * 64; i += blockDim.x) {
+    const int n = n0 + (i & 63);
+    wsm[i] = n < Cout ? Wp[(long long)(i >> 6) * Cout + n] : 0.f;
+  }
+  __syncthreads();
+  const long long HW = (long long)H * W;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)B * HW) return;
+  const int b = (int)(pix / HW);
+  const int r = (int)(pix - (long long)b * HW);
+  const int oh = r / W, ow = r - oh * W;
+  float acc[64];
+#pragma unroll
+  for (int n = 0; n < 64; ++n) acc[n] = (n0 + n < Cout) ? bias[n0 + n] : 0.f;
+  int kbase = 0;
+  for (int s = 0; s < 2; ++s) {
+    const float* src = s == 0 ? x : cond;
+    const int C = s == 0 ? Cx : Cc;
+    if (C == 0) continue;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ih = oh + tap / 3 - 1, iw = ow + tap % 3 - 1;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        const float* sp = src + ((long long)b * C * H + ih) * W + iw;
+        for (int c = 0; c < C; ++c) {
+          const float v = __ldg(sp + (long long)c * HW);
+          const float4* wr = reinterpret_cast<const float4*>(wsm + (kbase + tap * C + c) * 64);
+#pragma unroll
+          for (int n4 = 0; n4 < 16; ++n4) {
+            const float4 w4 = wr[n4];
+            acc[4 * n4] = fmaf(v, w4.x, acc[4 * n4]);
+            acc[4 * n4 + 1] = fmaf(v, w4.y, acc[4 * n4 + 1]);
+            acc[4 * n4 + 2] = fmaf(v, w4.z, acc[4 * n4 + 2]);
+            acc[4 * n4 + 3] = fmaf(v, w4.w, acc[4 * n4 + 3]);
+          }
+        }
+      }
+    }
+    kbase += 9 * C;
+  }
+  OutT* op = out + pix * Cout + n0;
+  if (n0 + 64 <= Cout && (Cout % 8) == 0) {
+    if (sizeof(OutT) == 2) {
+#pragma unroll
+      for (int n = 0; n < 64; n += 8) {
+        uint4 q;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(acc[n + 2 * e], acc[n + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(op) + n) = q;
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < 64; n += 4)
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(op) + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int n = 0; n < 64; ++n)
+      if (n0 + n < Cout) op[n] = from_float<OutT>(acc[n]);
+  }
+}
+}  // namespace
+
+int launch_conv_stem(const float* x, int Cx, const float* cond, int Cc, const float* Wp, const float* bias,
+                     void* out, int out_dt, int B, int H, int W, int Cout, cudaStream_t st) {
+  const int K = 9 * (Cx + Cc);
+  size_t smem = (size_t)K * 64 * sizeof(float);
+  EO_REQUIRE(smem <= 200 * 1024, EO_ERR_ARG, "conv_stem: %d input channels do not fit the shared-memory weight slice",
+             Cx + Cc);
+  dim3 grid((unsigned)ceil_div((long long)B * H * W, 128), (unsigned)ceil_div(Cout, 64));
+  if (out_dt == DT_BF16) {
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_conv_stem<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_conv_stem<__nv_bfloat16><<<grid, 128, smem, st>>>(x, Cx, cond, Cc, Wp, bias, reinterpret_cast<__nv_bfloat16*>(out),
+                                                       B, H, W, Cout);
+  } else {
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_conv_stem<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_conv_stem<float><<<grid, 128, smem, st>>>(x, Cx, cond, Cc, Wp, bias, reinterpret_cast<float*>(out), B, H, W, Cout);
+  }
   EO_CHECK_LAUNCH();
   return EO_OK;
 }
@@ -178,63 +334,101 @@ int launch_conv_simt(const ConvSimtParams& p, cudaStream_t st) {
 // GN scale/shift staged in shared memory; 16-byte (8 x bf16) loads along C.
 // =======================================================================================
 namespace {
+__device__ __forceinline__ void unpack8(const uint4& q, float f[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {          // bf16 -> fp32 is a 16-bit shift
+    f[2 * e] = __uint_as_float(w[e] << 16);
+    f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
+
+// One thread computes TWO horizontally adjacent output pixels x NACC output channels.  The 3x3
+// windows of the pair share a 3 x 4 pixel patch (12 instead of 18 16-byte loads per 8 channels);
+// the weights sit in shared memory as [tap][c][NACC] so one broadcast LDS.128 feeds 4 output
+// channels of both pixels.
 template <int NACC>
 __global__ void __launch_bounds__(128) k_conv_small_n(const ConvSmallNParams p) {
-  extern __shared__ float smem[];
-  float* wsm = smem;                       // [9*C][Cout]
-  float* sc = smem + 9 * p.C * p.Cout;     // [C]
-  float* sh = sc + p.C;                    // [C]
+  extern __shared__ __align__(16) float smem[];
+  float* wsm = smem;                        // [9*C][NACC], zero padded
+  float* sc = smem + 9 * p.C * NACC;        // [C]
+  float* sh = sc + p.C;                     // [C]
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 9 * p.C * p.Cout; i += blockDim.x) wsm[i] = p.Wp[i];
-  for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 9 * p.C * NACC; i += blockDim.x) {
+    const int n = i % NACC, k = i / NACC;
+    wsm[i] = n < p.Cout ? p.Wp[k * p.Cout + n] : 0.f;
+  }
+  const bool fold = p.gn_scale != nullptr;   // GroupNorm + SiLU folded into the load (else: pre-applied)
+  for (int i = threadIdx.x; i < p.C && fold; i += blockDim.x) {
     sc[i] = p.gn_scale[(long long)b * p.C + i];
     sh[i] = p.gn_shift[(long long)b * p.C + i];
   }
   __syncthreads();
   const int HW = p.H * p.W;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= HW) return;
-  const int oh = pix / p.W, ow = pix - oh * p.W;
-  float acc[NACC];
+  const int Wp2 = (p.W + 1) >> 1;
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= p.H * Wp2) return;
+  const int oh = pair / Wp2, ow = (pair - oh * Wp2) * 2;
+  float acc[2][NACC];
 #pragma unroll
-  for (int n = 0; n < NACC; ++n) acc[n] = 0.f;
-  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x);
-  for (int tap = 0; tap < 9; ++tap) {
-    int ih = oh + tap / 3 - 1, iw = ow + tap % 3 - 1;
-    if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) continue;
-    const uint4* row = reinterpret_cast<const uint4*>(x + (((long long)b * p.H + ih) * p.W + iw) * p.C);
-    const float* wt = wsm + tap * p.C * p.Cout;
-    for (int c8 = 0; c8 < p.C / 8; ++c8) {
-      uint4 q = __ldg(row + c8);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+  for (int q = 0; q < 2; ++q)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __bfloat1622float2(h2[e]);
-        int c = c8 * 8 + e * 2;
-        float v0 = silu_f(f.x * sc[c] + sh[c]);
-        float v1 = silu_f(f.y * sc[c + 1] + sh[c + 1]);
+    for (int n = 0; n < NACC; ++n) acc[q][n] = 0.f;
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + (long long)b * HW * p.C;
+  const int C8 = p.C / 8;
+  for (int r = 0; r < 3; ++r) {
+    const int ih = oh + r - 1;
+    if (ih < 0 || ih >= p.H) continue;
+    const uint4* rowp = reinterpret_cast<const uint4*>(x + (long long)ih * p.W * p.C);
+    for (int c8 = 0; c8 < C8; ++c8) {
+      float f[4][8];
 #pragma unroll
-        for (int n = 0; n < NACC; ++n) {
-          if (n < p.Cout) {
-            acc[n] = fmaf(v0, wt[c * p.Cout + n], acc[n]);
-            acc[n] = fmaf(v1, wt[(c + 1) * p.Cout + n], acc[n]);
+      for (int col = 0; col < 4; ++col) {
+        const int iw = ow - 1 + col;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (iw >= 0 && iw < p.W) q = __ldg(rowp + (long long)iw * C8 + c8);
+        unpack8(q, f[col]);
+        if (fold && iw >= 0 && iw < p.W) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[col][e] = silu_f(fmaf(f[col][e], sc[c8 * 8 + e], sh[c8 * 8 + e]));
+        }
+      }
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const float* wt = wsm + ((r * 3 + dw) * p.C + c8 * 8) * NACC;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+#pragma unroll
+          for (int n4 = 0; n4 < NACC; n4 += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wt + e * NACC + n4);
+            const float a0 = f[dw][e], a1 = f[dw + 1][e];
+            acc[0][n4] = fmaf(a0, w4.x, acc[0][n4]);         acc[1][n4] = fmaf(a1, w4.x, acc[1][n4]);
+            acc[0][n4 + 1] = fmaf(a0, w4.y, acc[0][n4 + 1]); acc[1][n4 + 1] = fmaf(a1, w4.y, acc[1][n4 + 1]);
+            acc[0][n4 + 2] = fmaf(a0, w4.z, acc[0][n4 + 2]); acc[1][n4 + 2] = fmaf(a1, w4.z, acc[1][n4 + 2]);
+            acc[0][n4 + 3] = fmaf(a0, w4.w, acc[0][n4 + 3]); acc[1][n4 + 3] = fmaf(a1, w4.w, acc[1][n4 + 3]);
           }
         }
       }
     }
   }
 #pragma unroll
-  for (int n = 0; n < NACC; ++n)
-    if (n < p.Cout) p.out_nchw[((long long)b * p.Cout + n) * HW + pix] = acc[n] + p.bias[n];
+  for (int q = 0; q < 2; ++q) {
+    if (ow + q >= p.W) continue;
+#pragma unroll
+    for (int n = 0; n < NACC; ++n)
+      if (n < p.Cout)
+        p.out_nchw[((long long)b * p.Cout + n) * HW + oh * p.W + ow + q] = acc[q][n] + p.bias[n];
+  }
 }
 }  // namespace
 
 int launch_conv_small_n(const ConvSmallNParams& p, cudaStream_t st) {
   EO_REQUIRE(p.dt == DT_BF16 && p.C % 8 == 0 && p.Cout <= 16, EO_ERR_ARG, "conv_small_n: shape");
-  size_t smem = (size_t)(9 * p.C * p.Cout + 2 * p.C) * sizeof(float);
+  const int nacc = p.Cout <= 4 ? 4 : 16;
+  size_t smem = (size_t)(9 * p.C * nacc + 2 * p.C) * sizeof(float);
   EO_REQUIRE(smem <= 200 * 1024, EO_ERR_ARG, "conv_small_n: weights do not fit shared memory");
-  dim3 grid((unsigned)ceil_div(p.H * p.W, 128), (unsigned)p.B);
-  if (p.Cout <= 4) {
+  dim3 grid((unsigned)ceil_div(p.H * ((p.W + 1) / 2), 128), (unsigned)p.B);
+  if (nacc == 4) {
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_conv_small_n<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_conv_small_n<4><<<grid, 128, smem, st>>>(p);
   } else {
@@ -251,27 +445,35 @@ int launch_conv_small_n(const ConvSmallNParams& p, cudaStream_t st) {
 namespace {
 struct GnSrcs { GnSrc s[2]; int n; };
 
-template <typename T> struct Vec4;
-template <> struct Vec4<float> {
+// 16-byte vector of T as floats: 4 x fp32 or 8 x bf16
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
   static __device__ __forceinline__ void load(const float* p, float v[4]) {
     float4 q = *reinterpret_cast<const float4*>(p);
     v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
   }
 };
-template <> struct Vec4<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float v[4]) {
-    uint2 q = *reinterpret_cast<const uint2*>(p);
-    float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&q.x));
-    float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&q.y));
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float v[8]) {
+    uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] = __uint_as_float(w[e] << 16);
+      v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
   }
 };
 
 // grid (chunks, B); each CTA reduces `ppc` pixels of sample b over all channels of all
 // sources into 32 (sum, sumsq) pairs, then adds them to sums[b] with 64 double atomics.
+// A thread owns one 16-byte channel vector and walks the pixels with 4 loads in flight.
 template <typename T, typename Acc>
 __global__ void __launch_bounds__(256)
 k_gn_stats(GnSrcs srcs, int HW, int ppc, int cpg, double* __restrict__ sums) {
+  constexpr int N = Vec16<T>::N;
   __shared__ double sm[64];
   const int tid = threadIdx.x, b = blockIdx.y;
   const int p0 = blockIdx.x * ppc, p1 = min(HW, p0 + ppc);
@@ -281,30 +483,44 @@ k_gn_stats(GnSrcs srcs, int HW, int ppc, int cpg, double* __restrict__ sums) {
   for (int s = 0; s < srcs.n; ++s) {
     const int C = srcs.s[s].C;
     const T* base = reinterpret_cast<const T*>(srcs.s[s].ptr) + (long long)b * HW * C;
-    const int ncol = C / 4;
+    const int ncol = C / N;
     const int rows = blockDim.x / ncol;   // >= 1 (C <= 1024)
     const int col = tid % ncol, row = tid / ncol;
     if (row < rows) {
-      Acc s4[4] = {0, 0, 0, 0}, q4[4] = {0, 0, 0, 0};
-      for (int p = p0 + row; p < p1; p += rows) {
-        float v[4];
-        Vec4<T>::load(base + (long long)p * C + col * 4, v);
+      Acc sv[N], qv[N];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { s4[j] += (Acc)v[j]; q4[j] += (Acc)v[j] * (Acc)v[j]; }
+      for (int j = 0; j < N; ++j) { sv[j] = 0; qv[j] = 0; }
+      const T* colp = base + col * N;
+      int p = p0 + row;
+      for (; p + 3 * rows < p1; p += 4 * rows) {       // 4 loads in flight per thread
+        float v[4][N];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Vec16<T>::load(colp + (long long)(p + u * rows) * C, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < N; ++j) { sv[j] += (Acc)v[u][j]; qv[j] += (Acc)v[u][j] * (Acc)v[u][j]; }
       }
-      const int c0 = coff + col * 4;
-      if ((cpg & 3) == 0) {
-        int g = c0 / cpg;
-        atomicAdd(&sm[2 * g], (double)s4[0] + (double)s4[1] + (double)s4[2] + (double)s4[3]);
-        atomicAdd(&sm[2 * g + 1], (double)q4[0] + (double)q4[1] + (double)q4[2] + (double)q4[3]);
-      } else {
+      for (; p < p1; p += rows) {
+        float v[N];
+        Vec16<T>::load(colp + (long long)p * C, v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int g = (c0 + j) / cpg;
-          atomicAdd(&sm[2 * g], (double)s4[j]);
-          atomicAdd(&sm[2 * g + 1], (double)q4[j]);
+        for (int j = 0; j < N; ++j) { sv[j] += (Acc)v[j]; qv[j] += (Acc)v[j] * (Acc)v[j]; }
+      }
+      // channels -> groups: merge runs of channels that fall into the same group
+      const int c0 = coff + col * N;
+      double rs = 0.0, rq = 0.0;
+      int g = c0 / cpg;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const int gj = (c0 + j) / cpg;
+        if (gj != g) {
+          atomicAdd(&sm[2 * g], rs); atomicAdd(&sm[2 * g + 1], rq);
+          rs = 0.0; rq = 0.0; g = gj;
         }
+        rs += (double)sv[j]; rq += (double)qv[j];
       }
+      atomicAdd(&sm[2 * g], rs); atomicAdd(&sm[2 * g + 1], rq);
     }
     coff += C;
   }
@@ -350,19 +566,32 @@ k_gn_apply(GnSrcs srcs, int HW, int ppc, int Ctot, const float* __restrict__ sca
         sc[j] = scale[(long long)b * Ctot + coff + col * 8 + j];
         sh[j] = shift[(long long)b * Ctot + coff + col * 8 + j];
       }
-      for (int p = p0 + row; p < p1; p += rows) {
-        uint4 q = *reinterpret_cast<const uint4*>(base + (long long)p * C + col * 8);
+      auto xform = [&](uint4 q) -> uint4 {
         __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float2 f = __bfloat1622float2(h2[e]);
-          f.x = f.x * sc[2 * e] + sh[2 * e];
-          f.y = f.y * sc[2 * e + 1] + sh[2 * e + 1];
+          f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
+          f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
           if (silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
           h2[e] = __floats2bfloat162_rn(f.x, f.y);
         }
-        *reinterpret_cast<uint4*>(dst + ((long long)b * HW + p) * Ctot + coff + col * 8) = q;
+        return q;
+      };
+      const __nv_bfloat16* src = base + col * 8;
+      __nv_bfloat16* out = dst + (long long)b * HW * Ctot + coff + col * 8;
+      int p = p0 + row;
+      for (; p + 3 * rows < p1; p += 4 * rows) {       // 4 loads in flight per thread
+        uint4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const uint4*>(src + (long long)(p + u * rows) * C);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(out + (long long)(p + u * rows) * Ctot) = xform(q[u]);
       }
+      for (; p < p1; p += rows)
+        *reinterpret_cast<uint4*>(out + (long long)p * Ctot) =
+            xform(*reinterpret_cast<const uint4*>(src + (long long)p * C));
     }
     coff += C;
   }
@@ -385,8 +614,9 @@ int launch_gn_stats(const GnSrc* src, int nsrc, int dt, int B, int HW, double* s
   int Ctot = 0;
   for (int i = 0; i < nsrc; ++i) {
     s.s[i] = src[i];
-    EO_REQUIRE(src[i].C % 4 == 0 && src[i].C <= 1024 && src[i].C > 0, EO_ERR_ARG,
-               "gn_stats: channels must be a multiple of 4 and <= 1024 (got %d)", src[i].C);
+    const int vec = dt == DT_F32 ? 4 : 8;
+    EO_REQUIRE(src[i].C % vec == 0 && src[i].C <= 256 * vec && src[i].C > 0, EO_ERR_ARG,
+               "gn_stats: channels must be a multiple of %d and <= %d (got %d)", vec, 256 * vec, src[i].C);
     Ctot += src[i].C;
   }
   EO_REQUIRE(Ctot % 32 == 0, EO_ERR_ARG, "gn_stats: channels %d not divisible by 32", Ctot);
