@@ -76,6 +76,7 @@ struct Act {   // NHWC activation living in the arena
   int C = 0, H = 0, W = 0;
   size_t bytes = 0;
   bool valid = false;
+  long long stats = -1;   // offset (floats) of this tensor's per-channel [Bmax][C][2] sums in ch_stats, or -1
 };
 
 struct WSpec {
@@ -135,6 +136,8 @@ struct eo_unet {
   float *w_emb_cat = nullptr, *b_emb_cat = nullptr;
   double* gn_sums = nullptr;
   int n_gn = 0;
+  double* ch_stats = nullptr;       // per-channel GroupNorm sums emitted by conv epilogues (zeroed per forward)
+  size_t ch_stats_floats = 0;       // element count
   // per-forward io (read by ops at launch time)
   const float* io_x = nullptr; int io_cx = 0;
   const float* io_cond = nullptr; int io_cc = 0;
@@ -153,7 +156,7 @@ struct eo_unet {
     arena_base = nullptr;
     ops.clear(); named.clear(); stem_split.clear();
     arena = Arena();
-    finalized = false; dev_bytes = 0; n_launches = 0; n_gn = 0;
+    finalized = false; dev_bytes = 0; n_launches = 0; n_gn = 0; ch_stats = nullptr; ch_stats_floats = 0;
     e0 = l1 = emb = tb = w_emb_cat = b_emb_cat = nullptr; gn_sums = nullptr;
     for (auto& ws : wspecs) ws.priv = nullptr;
   }
@@ -352,11 +355,20 @@ struct eo_unet {
     g.bytes = (size_t)Bmax * g.C * sizeof(float);
     g.scale_off = new_scratch(g.bytes);
     g.shift_off = new_scratch(g.bytes);
-    const int gi = n_gn++;
     const int HW = a.H * a.W;
     Act aa = a; Act bb = b ? *b : Act();
     const bool two = b != nullptr;
     const int dt = act_dt;
+    if (a.stats >= 0 && (!two || b->stats >= 0)) {
+      // every source carries per-channel sums written by its producer's epilogue: no extra read
+      push(name + ".gn", [=](int B, cudaStream_t st) -> int {
+        return launch_gn_finalize_ch(ch_stats + aa.stats, aa.C, two ? ch_stats + bb.stats : nullptr, two ? bb.C : 0,
+                                     gamma, beta, B, HW, ptr<float>(g.scale_off), ptr<float>(g.shift_off), st);
+      });
+      note("k_gn_finalize_ch", 0, 0);
+      return g;
+    }
+    const int gi = n_gn++;
     push(name + ".gn", [=](int B, cudaStream_t st) -> int {
       GnSrc s[2];
       s[0].ptr = ptr(aa.off); s[0].C = aa.C;
@@ -436,13 +448,17 @@ struct eo_unet {
   }
   int plan_conv_tc(const std::string& name, const std::vector<TcSegSpec>& tsegs, const std::vector<PackSeg>& segs,
                    int Cout_rows, const int* d_row_map, const float* bias_a, const float* bias_b, int tb_off,
-                   const Act* residual, int Ho, int Wo, Act* out, cudaStream_t st) {
+                   const Act* residual, int Ho, int Wo, Act* out, cudaStream_t st, bool want_stats = true) {
     void* Wp = nullptr; int K = 0;
     int rc = pack_tc(segs, Cout_rows, d_row_map, &Wp, &K, st);
     if (rc) return rc;
     float* bias = nullptr;
     if (bias_a || bias_b) { rc = pack_bias2(bias_a, bias_b, Cout_rows, d_row_map, &bias, st); if (rc) return rc; }
     Act o = new_act(Cout_rows, Ho, Wo);
+    if (want_stats && tc_conv_stats_supported(Ho, Wo)) {
+      o.stats = (long long)ch_stats_floats;
+      ch_stats_floats += (size_t)Bmax * Cout_rows * 2;
+    }
     Act res = residual ? *residual : Act();
     const bool has_res = residual != nullptr;
     std::vector<TcSegSpec> tv = tsegs;
@@ -462,6 +478,7 @@ struct eo_unet {
       if (tb_off >= 0) { p.bias_nc = tb + tb_off; p.ld_bias_nc = tb_total; }
       p.residual = has_res ? ptr(res.off) : nullptr;
       p.out = ptr(o.off);
+      p.stats = o.stats >= 0 ? ch_stats + o.stats : nullptr;
       return tc_conv_plan_create(p, &tc_plans[plan_idx]);
     };
     push(name, [=](int B, cudaStream_t stx) -> int { return tc_conv_launch(tc_plans[plan_idx], B, stx); }, 1, prepare);
@@ -593,7 +610,7 @@ struct eo_unet {
       EO_CHECK_CUDA(cudaStreamSynchronize(st));   // rmap is a stack-lifetime host buffer
       Act qkv;
       rc = plan_conv_tc(p + "qkv", {seg1x1(xn)}, {{wq, C, 1, 0, C}}, rows, d_rmap, w(p + "qkv.bias"), nullptr, -1, nullptr,
-                        x.H, x.W, &qkv, st);
+                        x.H, x.W, &qkv, st, /*want_stats=*/false);
       if (rc) return rc;
       free_act(xn);
       Act a = new_act(C, x.H, x.W);
@@ -815,6 +832,15 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
     });
     (void)cin;
     note(stem_kernel ? "k_conv_stem" : "k_conv_simt", 2.0 * H * W * cout * K, 0);
+    if (mode == EO_MODE_BF16 && cout % 8 == 0) {
+      h.stats = (long long)ch_stats_floats;
+      ch_stats_floats += (size_t)Bmax * cout * 2;
+      Act hc = h;
+      push("input_blocks.0.stats", [=](int B, cudaStream_t s) -> int {
+        return launch_chan_stats(ptr(hc.off), B, hc.H * hc.W, hc.C, ch_stats + hc.stats, s);
+      });
+      note("k_chan_stats", 0, (double)H * W * cout * 2);
+    }
   }
   named[in_blocks[0].name] = h;
 
@@ -872,6 +898,7 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
 
   // ---- allocate persistent GN accumulators and the arena, then prepare TC plans
   if ((rc = dmalloc(&gn_sums, (size_t)std::max(n_gn, 1) * Bmax * 64))) return rc;
+  if ((rc = dmalloc(&ch_stats, std::max<size_t>(ch_stats_floats, 4)))) return rc;
   {
     void* p = nullptr;
     EO_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(arena.peak, 1024)));
@@ -898,6 +925,7 @@ int eo_unet::forward(const float* x, int Cx, const float* cond, int Cc, const in
              "must specify y if and only if the model is class-conditional");
   io_x = x; io_cx = Cx; io_cond = cond; io_cc = Cc; io_t = t; io_y = y; io_out = out;
   EO_CHECK_CUDA(cudaMemsetAsync(gn_sums, 0, (size_t)std::max(n_gn, 1) * Bmax * 64 * sizeof(double), st));
+  if (ch_stats_floats) EO_CHECK_CUDA(cudaMemsetAsync(ch_stats, 0, ch_stats_floats * sizeof(double), st));
   std::vector<cudaEvent_t> ev;
   if (ms_per_op) {   // profiling variant: one CUDA event between consecutive ops, on `st`
     ev.resize(ops.size() + 1);
@@ -1058,7 +1086,7 @@ int eo_unet_op_info(const eo_unet* u, int index, const char** name, const char**
 }
 
 int64_t eo_unet_device_bytes(const eo_unet* u) { return u ? u->dev_bytes : 0; }
-int eo_unet_launches_per_forward(const eo_unet* u) { return u ? u->n_launches + 1 : 0; }   // + the GN memset
+int eo_unet_launches_per_forward(const eo_unet* u) { return u ? u->n_launches + 2 : 0; }   // + the two GN memsets
 
 int64_t eo_unet_read_activation(eo_unet* u, const char* name, float* out_dev, int64_t capacity, int B, void* stream) {
   EO_REQUIRE(u && name && out_dev, EO_ERR_ARG, "eo_unet_read_activation: null argument");

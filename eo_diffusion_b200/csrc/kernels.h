@@ -72,6 +72,11 @@ int launch_gn_stats(const GnSrc* src, int nsrc, int dt, int B, int HW, double* s
 // scale[b,c] = rstd*gamma[c]; shift[b,c] = beta[c] - mean*rstd*gamma[c]   (C = total channels)
 int launch_gn_finalize(const double* sums, const float* gamma, const float* beta, int B, int C,
                        int HW, float* scale, float* shift, cudaStream_t st);
+// per-channel (sum, sum of squares) of a bf16 NHWC tensor, added into stats[b][c][2]
+int launch_chan_stats(const void* x_bf16, int B, int HW, int C, double* stats, cudaStream_t st);
+// scale/shift from the per-channel sums of one or two channel-concatenated tensors
+int launch_gn_finalize_ch(const double* sa, int Ca, const double* sb, int Cb, const float* gamma, const float* beta,
+                          int B, int HW, float* scale, float* shift, cudaStream_t st);
 // dst[b,p,off_s + c] = act(src_s[b,p,c]*scale[b,off_s+c] + shift[b,off_s+c])   (bf16 -> bf16)
 int launch_gn_apply(const GnSrc* src, int nsrc, int B, int HW, const float* scale,
                     const float* shift, int silu, void* dst, cudaStream_t st);
@@ -142,9 +147,15 @@ struct TcConvParams {
   const float* bias = nullptr;      // [Cout] or null
   const float* bias_nc = nullptr;   // [B, ld_bias_nc] or null
   int ld_bias_nc = 0;
-  const void* residual = nullptr;   // bf16 NHWC [B,H,W,Cout] or null
-  void* out = nullptr;              // bf16 NHWC [B,H,W,Cout]
+  const void* residual = nullptr;   // NHWC [B,H,W,Cout] (fp32 if res_f32, else bf16) or null
+  int res_f32 = 0;
+  void* out = nullptr;              // NHWC [B,H,W,Cout] (fp32 if out_f32, else bf16)
+  int out_f32 = 0;
+  double* stats = nullptr;          // [B, Cout, 2] per-channel (sum, sum of squares) of `out`,
+                                    // accumulated with atomics (zeroed by the caller), or null
 };
+// fused statistics need a warp's 32 output rows inside one image
+bool tc_conv_stats_supported(int H, int W);
 // A prepared launch (tensor maps encoded once at plan time)
 struct TcConvPlan;
 int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out);

@@ -528,6 +528,62 @@ k_gn_stats(GnSrcs srcs, int HW, int ppc, int cpg, double* __restrict__ sums) {
   if (tid < 64) atomicAdd(&sums[(long long)b * 64 + tid], sm[tid]);
 }
 
+// Per-channel (sum, sum of squares) of one NHWC bf16 tensor -> stats[b][c][2] (fp32 atomics), for
+// tensors that are not written by the tensor-core conv (whose epilogue emits the same sums).
+__global__ void __launch_bounds__(256)
+k_chan_stats(const __nv_bfloat16* __restrict__ x, int C, int HW, int ppc, double* __restrict__ stats) {
+  extern __shared__ double sm[];    // [C][2]; double so that the atomic order does not show in the result
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const int p0 = blockIdx.x * ppc, p1 = min(HW, p0 + ppc);
+  for (int i = tid; i < 2 * C; i += blockDim.x) sm[i] = 0.0;
+  __syncthreads();
+  const __nv_bfloat16* base = x + (long long)b * HW * C;
+  const int ncol = C / 8;
+  const int rows = blockDim.x / ncol;
+  const int col = tid % ncol, row = tid / ncol;
+  if (row < rows) {
+    float sv[8], qv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sv[j] = 0.f; qv[j] = 0.f; }
+    for (int p = p0 + row; p < p1; p += rows) {
+      float v[8];
+      Vec16<__nv_bfloat16>::load(base + (long long)p * C + col * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sv[j] += v[j]; qv[j] = fmaf(v[j], v[j], qv[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm[(col * 8 + j) * 2], (double)sv[j]);
+      atomicAdd(&sm[(col * 8 + j) * 2 + 1], (double)qv[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += blockDim.x) atomicAdd(stats + (long long)b * C * 2 + i, sm[i]);
+}
+
+// GroupNorm scale/shift from per-channel sums of one or two concatenated tensors
+__global__ void k_gn_finalize_ch(const double* __restrict__ sa, int Ca, const double* __restrict__ sb, int Cb,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, int B,
+                                 int HW, float* __restrict__ scale, float* __restrict__ shift) {
+  const int C = Ca + Cb;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const int cpg = C / 32, g0 = (c / cpg) * cpg;
+  double s = 0.0, q = 0.0;
+  for (int k = g0; k < g0 + cpg; ++k) {
+    const double* src = k < Ca ? sa + ((long long)b * Ca + k) * 2 : sb + ((long long)b * Cb + (k - Ca)) * 2;
+    s += src[0]; q += src[1];
+  }
+  const double n = (double)cpg * (double)HW;
+  const double mean = s / n;
+  double var = q / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + 1e-5);
+  scale[i] = (float)(rstd * (double)gamma[c]);
+  shift[i] = (float)((double)beta[c] - mean * rstd * (double)gamma[c]);
+}
+
 __global__ void k_gn_finalize(const double* __restrict__ sums, const float* __restrict__ gamma,
                               const float* __restrict__ beta, int B, int C, int HW,
                               float* __restrict__ scale, float* __restrict__ shift) {
@@ -632,6 +688,24 @@ int launch_gn_finalize(const double* sums, const float* gamma, const float* beta
                        int HW, float* scale, float* shift, cudaStream_t st) {
   k_gn_finalize<<<(unsigned)ceil_div((long long)B * C, 256), 256, 0, st>>>(sums, gamma, beta, B, C,
                                                                           HW, scale, shift);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+
+int launch_chan_stats(const void* x_bf16, int B, int HW, int C, double* stats, cudaStream_t st) {
+  EO_REQUIRE(C % 8 == 0 && C <= 2048, EO_ERR_ARG, "chan_stats: channels");
+  int ppc = pick_ppc(B, HW);
+  dim3 grid((unsigned)ceil_div(HW, ppc), (unsigned)B);
+  k_chan_stats<<<grid, 256, 2 * C * sizeof(double), st>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), C, HW, ppc, stats);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+
+int launch_gn_finalize_ch(const double* sa, int Ca, const double* sb, int Cb, const float* gamma, const float* beta,
+                          int B, int HW, float* scale, float* shift, cudaStream_t st) {
+  EO_REQUIRE((Ca + Cb) % 32 == 0, EO_ERR_ARG, "gn_finalize_ch: channels %d not divisible by 32", Ca + Cb);
+  k_gn_finalize_ch<<<(unsigned)ceil_div((long long)B * (Ca + Cb), 256), 256, 0, st>>>(sa, Ca, sb, Cb, gamma, beta, B, HW,
+                                                                                     scale, shift);
   EO_CHECK_LAUNCH();
   return EO_OK;
 }

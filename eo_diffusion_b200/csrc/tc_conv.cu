@@ -23,6 +23,7 @@
 // Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2 * M * Cout * Ktot.
 #include "kernels.h"
 #include "tc_common.cuh"
+#include <cstdlib>
 #include <vector>
 
 namespace eo {
@@ -37,58 +38,91 @@ struct TileGeom {
   int H, W;
 };
 
+struct Epi {
+  const float* bias;        // [Cout] or null
+  const float* bias_nc;     // [B, ld_bias_nc] or null
+  int ld_bias_nc;
+  const void* residual;     // NHWC [B,H,W,Cout], fp32 if res_f32 else bf16, or null
+  void* out;                // NHWC [B,H,W,Cout], fp32 if out_f32 else bf16
+  double* stats;            // [B, Cout, 2] (sum, sum of squares) accumulated with atomics, or null
+  int Cout, res_f32, out_f32;
+};
+
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 
-template <int BN, int STAGES>
+// BN = N extent of the accumulator tile.  PAIR: two CTAs (a cluster of 2 on one TPC) compute a
+// 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 pixel rows of A and HALF of
+// the BN weight rows, so the shared-memory traffic per MMA drops by a third to a half.
+template <int BN, int STAGES, bool PAIR>
 struct SmemLayout {
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_BYTES;
   static constexpr int TAB_OFF = B_OFF + STAGES * B_BYTES;
   static constexpr int MAX_KB = 192;
-  static constexpr int BAR_OFF = TAB_OFF + MAX_KB * 16;
+  static constexpr int STAT_OFF = TAB_OFF + MAX_KB * 16;          // [4 warps][BN][2] floats
+  static constexpr int BAR_OFF = STAT_OFF + 4 * BN * 2 * 4;
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for manual 1024 B alignment
 };
 
-template <int BN, int STAGES>
+// column sums over the 32 lanes of a warp: on return lane j holds sum_over_lanes(f[j]).
+// Recursive halving: 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_column_sums(float (&f)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float keep = upper ? f[i + off] : f[i];
+      const float send = upper ? f[i] : f[i + off];
+      f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return f[0];
+}
+
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(192, 2)
 k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
-          const KBlk* __restrict__ kblks, int nkb, TileGeom g, int B,
-          const float* __restrict__ bias, const float* __restrict__ bias_nc, int ld_bias_nc,
-          const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, int Cout) {
-  using L = SmemLayout<BN, STAGES>;
+          const KBlk* __restrict__ kblks, int nkb, TileGeom g, int B, Epi ep) {
+  using L = SmemLayout<BN, STAGES, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
   KBlk* tab = reinterpret_cast<KBlk*>(smem + L::TAB_OFF);
+  float* sstat = reinterpret_cast<float*>(smem + L::STAT_OFF);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&mapA0);
     tc::tma_prefetch_desc(&mapB);
+    // full: one arrival (the leader's producer, which also posts the byte count of BOTH CTAs' loads;
+    // the peer's TMA only completes transactions on it) -- only the leader's copy is used
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(tmem_full, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_ptr, BN);
-    tc::tmem_relinquish();
+    if (PAIR) { tc::tmem_alloc2(tmem_ptr, BN); tc::tmem_relinquish2(); }
+    else { tc::tmem_alloc(tmem_ptr, BN); tc::tmem_relinquish(); }
   }
   for (int i = threadIdx.x; i < nkb; i += blockDim.x) tab[i] = kblks[i];
   tc::tc_fence_before();
-  __syncthreads();
+  if (PAIR) tc::cluster_sync_all(); else __syncthreads();   // peer barriers are initialised past here
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // tile coordinates
+  // tile coordinates (the two CTAs of a pair take consecutive pixel tiles)
   const int mt = blockIdx.x;
   const int tw = mt % g.tiles_w;
   const int th = (mt / g.tiles_w) % g.tiles_h;
@@ -98,22 +132,32 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 
   if (warp == 0) {
     if (lane == 0) {
+      const uint32_t full0 = tc::smem_u32(&full[0]);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         tc::mbar_wait(&empty[s], ph ^ 1);
-        tc::mbar_arrive_expect_tx(&full[s], A_BYTES + L::B_BYTES);
         const KBlk e = tab[kb];
         const int dh = (int)(short)(e.dh_dw & 0xffff), dw = (int)(short)(e.dh_dw >> 16);
         const CUtensorMap* ma = e.seg == 0 ? &mapA0 : (e.seg == 1 ? &mapA1 : &mapA2);
-        tc::tma_load_4d(smem + L::A_OFF + s * A_BYTES, ma, &full[s], e.c0, w0 + dw, h0 + dh,
-                        n0 + e.dn);
-        tc::tma_load_2d(smem + L::B_OFF + s * L::B_BYTES, &mapB, &full[s], kb * BK, nbase);
+        if (PAIR) {
+          const uint32_t lbar = tc::mapa_u32(full0 + s * 8, 0);       // the leader's full[s]
+          // The peer's bytes for this phase can only be issued after the leader's MMA released the
+          // slot (multicast commit), i.e. after the previous phase completed; if they land before the
+          // leader arms the phase the transaction count just goes negative until expect_tx.
+          if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], 2 * (A_BYTES + L::B_BYTES));
+          tc::tma2_load_4d(smem + L::A_OFF + s * A_BYTES, ma, lbar, e.c0, w0 + dw, h0 + dh, n0 + e.dn);
+          tc::tma2_load_2d(smem + L::B_OFF + s * L::B_BYTES, &mapB, lbar, kb * BK, nbase + (int)rank * L::B_ROWS);
+        } else {
+          tc::mbar_arrive_expect_tx(&full[s], A_BYTES + L::B_BYTES);
+          tc::tma_load_4d(smem + L::A_OFF + s * A_BYTES, ma, &full[s], e.c0, w0 + dw, h0 + dh, n0 + e.dn);
+          tc::tma_load_2d(smem + L::B_OFF + s * L::B_BYTES, &mapB, &full[s], kb * BK, nbase);
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(PAIR ? 2 * BM : BM, BN, 0, 0);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -123,15 +167,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         const uint64_t bdesc = tc::make_sw128_desc(tc::smem_u32(smem + L::B_OFF + s * L::B_BYTES));
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          tc::umma_f16_ss(tmem_base, tc::desc_advance(adesc, k * 32), tc::desc_advance(bdesc, k * 32),
-                          idesc, (kb | k) != 0 ? 1u : 0u);
+          if (PAIR) tc::umma2_f16_ss(tmem_base, tc::desc_advance(adesc, k * 32), tc::desc_advance(bdesc, k * 32),
+                                     idesc, (kb | k) != 0 ? 1u : 0u);
+          else tc::umma_f16_ss(tmem_base, tc::desc_advance(adesc, k * 32), tc::desc_advance(bdesc, k * 32),
+                               idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        tc::umma_commit(&empty[s]);       // frees the smem stage when these MMAs retire
+        // frees the smem stage (in both CTAs) when these MMAs retire
+        if (PAIR) tc::umma2_commit_mc(&empty[s], 3); else tc::umma_commit(&empty[s]);
       }
-      tc::umma_commit(tmem_full);         // accumulator complete
+      if (PAIR) tc::umma2_commit_mc(tmem_full, 3); else tc::umma_commit(tmem_full);   // accumulator complete
     }
   } else {
-    // ---- epilogue: TMEM -> registers -> (+bias, +per-sample bias, +residual) -> bf16 -> HBM
+    // ---- epilogue: TMEM -> registers -> (+bias, +per-sample bias, +residual) -> HBM [+ GN partial sums]
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int ww = row % g.bw;
@@ -140,7 +187,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     const int n_img = n0 + nn;
     const bool valid = n_img < B;
     const long long pix = ((long long)n_img * g.H + (h0 + hh)) * g.W + (w0 + ww);
-    const float* bnc = (bias_nc && valid) ? bias_nc + (long long)n_img * ld_bias_nc : nullptr;
+    const float* bnc = (ep.bias_nc && valid) ? ep.bias_nc + (long long)n_img * ep.ld_bias_nc : nullptr;
+    const int Cout = ep.Cout;
+    // statistics need a warp's 32 rows inside one image (host guarantees bw*bh >= 32 when stats != null)
+    const bool do_stats = ep.stats != nullptr;
+    const bool warp_valid = __shfl_sync(0xffffffffu, valid ? 1 : 0, 0) != 0;
     tc::mbar_wait(tmem_full, 0);
     tc::tc_fence_after();
 #pragma unroll 1
@@ -149,14 +200,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tc::tmem_ld_wait();
       const int n = nbase + c0;
-      if (valid && n < Cout) {
-        float f[32];
+      if (n >= Cout) continue;             // warp-uniform
+      float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (bias) {
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (valid) {
+        if (ep.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + j));
+            float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
             f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
           }
         }
@@ -168,37 +220,84 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           }
         }
         const long long o = pix * Cout + n;
-        if (residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(residual + o);
+        if (ep.residual) {
+          if (ep.res_f32) {
+            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) + o);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 r = __ldg(rp + j);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+            for (int j = 0; j < 8; ++j) {
+              float4 r = __ldg(rp + j);
+              f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+            }
+          } else {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + o);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 t = __bfloat1622float2(h2[e]);
-              f[j * 8 + e * 2] += t.x; f[j * 8 + e * 2 + 1] += t.y;
+            for (int j = 0; j < 4; ++j) {
+              uint4 r = __ldg(rp + j);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 t = __bfloat1622float2(h2[e]);
+                f[j * 8 + e * 2] += t.x; f[j * 8 + e * 2 + 1] += t.y;
+              }
             }
           }
         }
-        uint4* op = reinterpret_cast<uint4*>(out + o);
+        if (ep.out_f32) {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + o);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 w;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
+          for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + o);
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            h2[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
-          op[j] = w;
+          for (int j = 0; j < 4; ++j) {
+            uint4 w;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              h2[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+            op[j] = w;
+          }
+        }
+      }
+      if (do_stats && warp_valid) {
+        // per-channel sum and sum of squares of this warp's 32 pixel rows (GroupNorm statistics of
+        // the tensor being written; reference nn.GroupNorm reduces them per group later)
+        float sq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+        const float cs = warp_column_sums(f, lane);
+        const float cq = warp_column_sums(sq, lane);
+        // Deterministic: every partial sum is formed in a fixed order in fp32; only the final
+        // accumulation across tiles is atomic, and that one is in double (order effects ~1e-16).
+        if (g.bn == 1) {                  // whole tile in one image: the 4 warps meet in smem first
+          sstat[(q * BN + c0 + lane) * 2] = cs;
+          sstat[(q * BN + c0 + lane) * 2 + 1] = cq;
+        } else {
+          double* dst = ep.stats + ((long long)n_img * Cout + n + lane) * 2;
+          atomicAdd(dst, (double)cs);
+          atomicAdd(dst + 1, (double)cq);
+        }
+      }
+    }
+    if (do_stats && g.bn == 1) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps
+      if (n0 < B) {
+        const int et = threadIdx.x - 64;                  // 0..127
+        for (int i = et; i < BN * 2; i += 128) {
+          const int c = nbase + (i >> 1);
+          if (c < Cout) {
+            const float tsum = (sstat[i] + sstat[BN * 2 + i]) + (sstat[2 * BN * 2 + i] + sstat[3 * BN * 2 + i]);
+            atomicAdd(ep.stats + ((long long)n0 * Cout + c) * 2 + (i & 1), (double)tsum);
+          }
         }
       }
     }
     tc::tc_fence_before();
   }
-  __syncthreads();
+  if (PAIR) tc::cluster_sync_all(); else __syncthreads();   // nobody leaves while the peer still uses its smem/TMEM
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, BN);
+    if (PAIR) tc::tmem_dealloc2(tmem_base, BN); else tc::tmem_dealloc(tmem_base, BN);
   }
 }
 
@@ -248,16 +347,30 @@ struct TcConvPlan {
   int nkb = 0;
   TileGeom g{};
   int bn_tile = 128;
+  bool pair = true;
   TcConvParams p;
 };
 
 static int floor_pow2(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
+
+static bool use_pairs() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("EO_CONV_1CTA"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v != 0;
+}
+
+bool tc_conv_stats_supported(int H, int W) {
+  int bw = floor_pow2(W < 16 ? W : 16);
+  int bh = floor_pow2(H < BM / bw ? H : BM / bw);
+  return bw * bh >= 32;
+}
 
 int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out) {
   EO_REQUIRE(p.nseg >= 1 && p.nseg <= 3, EO_ERR_ARG, "tc_conv: nseg");
   EO_REQUIRE(p.Cout % 64 == 0, EO_ERR_ARG, "tc_conv: Cout %d must be a multiple of 64", p.Cout);
   TcConvPlan* pl = new TcConvPlan();
   pl->p = p;
+  pl->pair = use_pairs();
   // ---- tile geometry: 128 pixels = bn x bh x bw
   TileGeom g;
   g.H = p.H; g.W = p.W;
@@ -267,6 +380,11 @@ int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out) {
   if (p.W % g.bw != 0 || p.H % g.bh != 0) {
     delete pl;
     set_error("tc_conv: feature map %dx%d is not tileable by %dx%d boxes", p.H, p.W, g.bh, g.bw);
+    return EO_ERR_ARG;
+  }
+  if (p.stats && g.bw * g.bh < 32) {
+    delete pl;
+    set_error("tc_conv: fused GroupNorm statistics need at least 32 pixels per image (%dx%d)", p.H, p.W);
     return EO_ERR_ARG;
   }
   g.tiles_w = p.W / g.bw; g.tiles_h = p.H / g.bh;
@@ -303,11 +421,9 @@ int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out) {
     return EO_ERR_ARG;
   }
   {
-    int cout_pad = (int)ceil_div(p.Cout, pl->bn_tile) * pl->bn_tile;
-    (void)cout_pad;
     uint64_t dims[2] = {(uint64_t)p.Ktot, (uint64_t)p.Cout};
     uint64_t str[1] = {(uint64_t)p.Ktot * 2};
-    uint32_t box[2] = {(uint32_t)BK, (uint32_t)pl->bn_tile};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)(pl->pair ? pl->bn_tile / 2 : pl->bn_tile)};
     int rc = encode_tmap_bf16(&pl->mapB, p.Wp, 2, dims, str, box);
     if (rc != EO_OK) { delete pl; return rc; }
   }
@@ -329,29 +445,45 @@ void tc_conv_plan_destroy(TcConvPlan* p) {
   delete p;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 static int launch_tc(const TcConvPlan* pl, int B, cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, PAIR>;
   static bool attr_set = false;
+  auto kern = k_conv_tc<BN, STAGES, PAIR>;
   if (!attr_set) {
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<BN, STAGES>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
   const TileGeom& g = pl->g;
+  const TcConvParams& p = pl->p;
   int tiles_n = (int)ceil_div(B, g.bn);
-  dim3 grid((unsigned)(g.tiles_w * g.tiles_h * tiles_n), (unsigned)ceil_div(pl->p.Cout, BN));
-  k_conv_tc<BN, STAGES><<<grid, 192, L::DYN_BYTES, st>>>(
-      pl->mapA[0], pl->mapA[1], pl->mapA[2], pl->mapB, pl->d_kblks, pl->nkb, g, B, pl->p.bias,
-      pl->p.bias_nc, pl->p.ld_bias_nc, reinterpret_cast<const __nv_bfloat16*>(pl->p.residual),
-      reinterpret_cast<__nv_bfloat16*>(pl->p.out), pl->p.Cout);
-  EO_CHECK_LAUNCH();
+  int mtiles = g.tiles_w * g.tiles_h * tiles_n;
+  if (PAIR) mtiles = (mtiles + 1) & ~1;      // an odd last tile gets an all-masked partner
+  Epi ep;
+  ep.bias = p.bias; ep.bias_nc = p.bias_nc; ep.ld_bias_nc = p.ld_bias_nc; ep.residual = p.residual;
+  ep.out = p.out; ep.stats = p.stats; ep.Cout = p.Cout; ep.res_f32 = p.res_f32; ep.out_f32 = p.out_f32;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)mtiles, (unsigned)ceil_div(p.Cout, BN));
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = L::DYN_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  EO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA[0], pl->mapA[1], pl->mapA[2], pl->mapB,
+                                   (const KBlk*)pl->d_kblks, pl->nkb, g, B, ep));
   return EO_OK;
 }
 
 int tc_conv_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
-  if (pl->bn_tile == 256) return launch_tc<256, 2>(pl, B, st);
-  return launch_tc<128, 3>(pl, B, st);
+  if (pl->pair) {
+    // per CTA and stage: 16 KB of A + BN/2 weight rows (16 or 8 KB); two CTAs stay co-resident per SM
+    if (pl->bn_tile == 256) return launch_tc<256, 3, true>(pl, B, st);
+    return launch_tc<128, 4, true>(pl, B, st);
+  }
+  if (pl->bn_tile == 256) return launch_tc<256, 2, false>(pl, B, st);
+  return launch_tc<128, 3, false>(pl, B, st);
 }
 
 }  // namespace eo

@@ -1,5 +1,5 @@
 """Top SASS instructions by stall samples from `ncu --page source --csv` (needs -lineinfo +
---import-source on).  usage: python profiles/src_hotspots.py prof.ncu-rep [N]"""
+--import-source on).  usage: python profiles/src_hotspots.py prof.ncu-rep [N] [launch index]"""
 import csv
 import subprocess
 import sys
@@ -10,7 +10,13 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 hdr = rows[1]
 col = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-body = [r for r in rows[2:] if len(r) == len(hdr)]
+# several launches: each has its own "Kernel Name" + header rows; keep the launch asked for
+launch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+lo = starts[launch] + 2
+hi = starts[launch + 1] if launch + 1 < len(starts) else len(rows)
+print(rows[starts[launch]][1][:100])
+body = [r for r in rows[lo:hi] if len(r) == len(hdr)]
 tot = sum(int(r[col["# Samples"]] or 0) for r in body)
 totinst = sum(int(r[col["Instructions Executed"]] or 0) for r in body)
 print(f"total samples {tot}, warp instructions executed {totinst}")
