@@ -65,6 +65,7 @@ SIGNATURES = {
     "eo_cfg_combine": (_I, [_P, _P, _F, _P, _L, _P]),
     "eo_test_conv_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "eo_test_attention_tc": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "eo_debug_conv_trace": (_I, [_P, _I]),
 }
 
 _lock = threading.Lock()

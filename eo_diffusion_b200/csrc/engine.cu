@@ -1135,6 +1135,11 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
   return rc;
 }
 
+int eo_debug_conv_trace(void* dev_buf, int n_ctas) {
+  tc_conv_set_trace(reinterpret_cast<long long*>(dev_buf), n_ctas);
+  return EO_OK;
+}
+
 int eo_test_attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int heads, int ch, void* stream) {
   int rc = eo_device_check();
   if (rc) return rc;

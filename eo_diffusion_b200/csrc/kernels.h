@@ -161,6 +161,8 @@ struct TcConvPlan;
 int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out);
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_launch(const TcConvPlan* plan, int B, cudaStream_t st);
+// development aid: per-CTA phase stamps of subsequent launches ([n_ctas][8] int64, device), null = off
+void tc_conv_set_trace(long long* dev_buf, int n_ctas);
 
 struct TcAttnParams {
   const void* qkv = nullptr;  // bf16 [B, T, heads*3*64]: per head q|k|v each padded to 64 channels

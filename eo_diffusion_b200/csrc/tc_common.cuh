@@ -44,6 +44,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// wait whose acquire covers arrivals made by threads of the peer CTA (mbarrier.arrive.release.cluster)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 24)) asm volatile("trap;");
+  }
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -202,6 +217,19 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;       // SBO
   d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+// Same, with an explicit stride between 8-row groups.  The swizzle XOR is a function of the absolute
+// shared-memory address bits [7,10) (probed on B200: tools/probe_shifted_desc.cu), so the start address
+// may be any multiple of 128 B inside a tile that TMA wrote with SWIZZLE_128B, and SBO any multiple of
+// 128 B: a shifted window of a halo patch is a valid operand.
+__device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
   return d;
 }
 // advance the start address by `bytes` (must keep bits [7,10) of the address consistent with

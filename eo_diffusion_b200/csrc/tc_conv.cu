@@ -23,6 +23,7 @@
 // Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2 * M * Cout * Ktot.
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "tc_conv_epi.cuh"
 #include <cstdlib>
 #include <vector>
 
@@ -38,15 +39,7 @@ struct TileGeom {
   int H, W;
 };
 
-struct Epi {
-  const float* bias;        // [Cout] or null
-  const float* bias_nc;     // [B, ld_bias_nc] or null
-  int ld_bias_nc;
-  const void* residual;     // NHWC [B,H,W,Cout], fp32 if res_f32 else bf16, or null
-  void* out;                // NHWC [B,H,W,Cout], fp32 if out_f32 else bf16
-  double* stats;            // [B, Cout, 2] (sum, sum of squares) accumulated with atomics, or null
-  int Cout, res_f32, out_f32;
-};
+using tc::Epi;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -69,22 +62,6 @@ struct SmemLayout {
   static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for manual 1024 B alignment
 };
 
-// column sums over the 32 lanes of a warp: on return lane j holds sum_over_lanes(f[j]).
-// Recursive halving: 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
-__device__ __forceinline__ float warp_column_sums(float (&f)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float keep = upper ? f[i + off] : f[i];
-      const float send = upper ? f[i] : f[i + off];
-      f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return f[0];
-}
-
 template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(192, 2)
 k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -102,6 +79,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
+  if (threadIdx.x == 0) { tc::trace_stamp(ep, 0); tc::trace_stamp(ep, 7); tc::trace_stamp(ep, 1); }
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&mapA0);
@@ -121,6 +99,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   if (PAIR) tc::cluster_sync_all(); else __syncthreads();   // peer barriers are initialised past here
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) tc::trace_stamp(ep, 2);
 
   // tile coordinates (the two CTAs of a pair take consecutive pixel tiles)
   const int mt = blockIdx.x;
@@ -163,6 +142,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         const uint32_t ph = (kb / STAGES) & 1;
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
+        if (kb == 0) tc::trace_stamp(ep, 3);
         const uint64_t adesc = tc::make_sw128_desc(tc::smem_u32(smem + L::A_OFF + s * A_BYTES));
         const uint64_t bdesc = tc::make_sw128_desc(tc::smem_u32(smem + L::B_OFF + s * L::B_BYTES));
 #pragma unroll
@@ -187,111 +167,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     const int n_img = n0 + nn;
     const bool valid = n_img < B;
     const long long pix = ((long long)n_img * g.H + (h0 + hh)) * g.W + (w0 + ww);
-    const float* bnc = (ep.bias_nc && valid) ? ep.bias_nc + (long long)n_img * ep.ld_bias_nc : nullptr;
-    const int Cout = ep.Cout;
-    // statistics need a warp's 32 rows inside one image (host guarantees bw*bh >= 32 when stats != null)
-    const bool do_stats = ep.stats != nullptr;
-    const bool warp_valid = __shfl_sync(0xffffffffu, valid ? 1 : 0, 0) != 0;
     tc::mbar_wait(tmem_full, 0);
     tc::tc_fence_after();
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tc::tmem_ld_wait();
-      const int n = nbase + c0;
-      if (n >= Cout) continue;             // warp-uniform
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (valid) {
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
-            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-          }
-        }
-        if (bnc) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b4 = __ldg(reinterpret_cast<const float4*>(bnc + n + j));
-            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-          }
-        }
-        const long long o = pix * Cout + n;
-        if (ep.residual) {
-          if (ep.res_f32) {
-            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) + o);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 r = __ldg(rp + j);
-              f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
-            }
-          } else {
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 r = __ldg(rp + j);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 t = __bfloat1622float2(h2[e]);
-                f[j * 8 + e * 2] += t.x; f[j * 8 + e * 2 + 1] += t.y;
-              }
-            }
-          }
-        }
-        if (ep.out_f32) {
-          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + o);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + o);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 w;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              h2[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
-            op[j] = w;
-          }
-        }
-      }
-      if (do_stats && warp_valid) {
-        // per-channel sum and sum of squares of this warp's 32 pixel rows (GroupNorm statistics of
-        // the tensor being written; reference nn.GroupNorm reduces them per group later)
-        float sq[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
-        const float cs = warp_column_sums(f, lane);
-        const float cq = warp_column_sums(sq, lane);
-        // Deterministic: every partial sum is formed in a fixed order in fp32; only the final
-        // accumulation across tiles is atomic, and that one is in double (order effects ~1e-16).
-        if (g.bn == 1) {                  // whole tile in one image: the 4 warps meet in smem first
-          sstat[(q * BN + c0 + lane) * 2] = cs;
-          sstat[(q * BN + c0 + lane) * 2 + 1] = cq;
-        } else {
-          double* dst = ep.stats + ((long long)n_img * Cout + n + lane) * 2;
-          atomicAdd(dst, (double)cs);
-          atomicAdd(dst + 1, (double)cq);
-        }
-      }
-    }
-    if (do_stats && g.bn == 1) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps
-      if (n0 < B) {
-        const int et = threadIdx.x - 64;                  // 0..127
-        for (int i = et; i < BN * 2; i += 128) {
-          const int c = nbase + (i >> 1);
-          if (c < Cout) {
-            const float tsum = (sstat[i] + sstat[BN * 2 + i]) + (sstat[2 * BN * 2 + i] + sstat[3 * BN * 2 + i]);
-            atomicAdd(ep.stats + ((long long)n0 * Cout + c) * 2 + (i & 1), (double)tsum);
-          }
-        }
-      }
-    }
+    if (threadIdx.x == 64) tc::trace_stamp(ep, 4);
+    // statistics need a warp's 32 rows inside one image (host guarantees bw*bh >= 32 when stats != null)
+    tc::conv_epilogue<BN>(tmem_base, q, lane, threadIdx.x - 64, nbase, valid, n_img, pix, ep, g.bn == 1, sstat);
+    if (threadIdx.x == 64) tc::trace_stamp(ep, 5);
     tc::tc_fence_before();
   }
   if (PAIR) tc::cluster_sync_all(); else __syncthreads();   // nobody leaves while the peer still uses its smem/TMEM
@@ -299,6 +180,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     tc::tc_fence_after();
     if (PAIR) tc::tmem_dealloc2(tmem_base, BN); else tc::tmem_dealloc(tmem_base, BN);
   }
+  if (threadIdx.x == 0) tc::trace_stamp(ep, 6);
 }
 
 }  // namespace
@@ -350,6 +232,10 @@ struct TcConvPlan {
   bool pair = true;
   TcConvParams p;
 };
+
+static long long* g_trace = nullptr;
+static int g_trace_n = 0;
+void tc_conv_set_trace(long long* dev_buf, int n_ctas) { g_trace = dev_buf; g_trace_n = n_ctas; }
 
 static int floor_pow2(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
 
@@ -462,6 +348,7 @@ static int launch_tc(const TcConvPlan* pl, int B, cudaStream_t st) {
   Epi ep;
   ep.bias = p.bias; ep.bias_nc = p.bias_nc; ep.ld_bias_nc = p.ld_bias_nc; ep.residual = p.residual;
   ep.out = p.out; ep.stats = p.stats; ep.Cout = p.Cout; ep.res_f32 = p.res_f32; ep.out_f32 = p.out_f32;
+  ep.trace = g_trace; ep.trace_n = g_trace_n;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)mtiles, (unsigned)ceil_div(p.Cout, BN));
   cfg.blockDim = dim3(192);

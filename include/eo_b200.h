@@ -209,6 +209,11 @@ EO_API int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias
 EO_API int eo_test_attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int heads, int ch,
                          void* stream);
 
+/* Development aid (tools/conv_trace.py): while dev_buf != NULL every tensor-core convolution launch
+ * writes, for its first n_ctas CTAs, eight int64 phase stamps (globaltimer at entry, clock64 at setup
+ * done / first operands landed / accumulator complete / epilogue done / exit, SM id).  NULL turns it off. */
+EO_API int eo_debug_conv_trace(void* dev_buf, int n_ctas);
+
 #ifdef __cplusplus
 }
 #endif
