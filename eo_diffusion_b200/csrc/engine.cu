@@ -446,9 +446,31 @@ struct eo_unet {
     TcSegSpec s; s.act = a; s.ntaps = 1; s.dh[0] = 0; s.dw[0] = 0; s.plane[0] = 0;
     return s;
   }
-  int plan_conv_tc(const std::string& name, const std::vector<TcSegSpec>& tsegs, const std::vector<PackSeg>& segs,
+  // a plain 3x3 window over one tensor: served from halo patches when the output grid allows it
+  static bool patchable(const TcSegSpec& s, int Ho, int Wo) {
+    if (s.ntaps != 9 || !tc_conv_patch_supported(Ho, Wo)) return false;
+    for (int t = 0; t < 9; ++t)
+      if (s.dh[t] != t / 3 - 1 || s.dw[t] != t % 3 - 1 || s.plane[t] != 0) return false;
+    return true;
+  }
+  // weights of a patch segment are K-ordered (64-channel block, tap, channel): one PackSeg per block
+  static std::vector<PackSeg> patch_order(const std::vector<PackSeg>& segs, const std::vector<bool>& patch) {
+    std::vector<PackSeg> o;
+    for (size_t i = 0; i < segs.size(); ++i) {
+      if (!patch[i]) { o.push_back(segs[i]); continue; }
+      for (int c0 = 0; c0 < segs[i].C; c0 += 64) {
+        PackSeg s = segs[i]; s.cin_off += c0; s.C = 64;
+        o.push_back(s);
+      }
+    }
+    return o;
+  }
+  int plan_conv_tc(const std::string& name, const std::vector<TcSegSpec>& tsegs, const std::vector<PackSeg>& segs_in,
                    int Cout_rows, const int* d_row_map, const float* bias_a, const float* bias_b, int tb_off,
                    const Act* residual, int Ho, int Wo, Act* out, cudaStream_t st, bool want_stats = true) {
+    std::vector<bool> patch;
+    for (auto& ts : tsegs) patch.push_back(patchable(ts, Ho, Wo) && ts.act.C % 64 == 0);
+    const std::vector<PackSeg> segs = patch_order(segs_in, patch);
     void* Wp = nullptr; int K = 0;
     int rc = pack_tc(segs, Cout_rows, d_row_map, &Wp, &K, st);
     if (rc) return rc;
@@ -469,7 +491,7 @@ struct eo_unet {
       p.nseg = (int)tv.size();
       for (int i = 0; i < p.nseg; ++i) {
         p.seg[i].ptr = ptr(tv[i].act.off); p.seg[i].C = tv[i].act.C;
-        p.seg[i].Bt = Bmax * tv[i].batch_mult; p.seg[i].ntaps = tv[i].ntaps;
+        p.seg[i].Bt = Bmax * tv[i].batch_mult; p.seg[i].ntaps = tv[i].ntaps; p.seg[i].patch = patch[i] ? 1 : 0;
         for (int t = 0; t < tv[i].ntaps; ++t) {
           p.seg[i].dh[t] = tv[i].dh[t]; p.seg[i].dw[t] = tv[i].dw[t]; p.seg[i].dn[t] = tv[i].plane[t] * Bmax;
         }
@@ -1112,7 +1134,13 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
   const int K = k * k * Cin;
   __nv_bfloat16* Wp = nullptr;
   EO_CHECK_CUDA(cudaMalloc(&Wp, (size_t)K * Cout * sizeof(__nv_bfloat16)));
-  rc = launch_pack_conv_weight(w, Cin, k, 0, Cin, Wp, DT_BF16, K, 1, 0, Cout, nullptr, st);
+  const bool patch = k == 3 && Cin % 64 == 0 && tc_conv_patch_supported(H, W);
+  if (patch) {   // K order (64-channel block, tap, channel)
+    for (int c0 = 0; c0 < Cin && !rc; c0 += 64)
+      rc = launch_pack_conv_weight(w, Cin, k, c0, 64, Wp, DT_BF16, K, 1, (c0 / 64) * 9 * 64, Cout, nullptr, st);
+  } else {
+    rc = launch_pack_conv_weight(w, Cin, k, 0, Cin, Wp, DT_BF16, K, 1, 0, Cout, nullptr, st);
+  }
   TcConvPlan* plan = nullptr;
   if (!rc) {
     TcConvParams p;
@@ -1123,6 +1151,7 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
       p.seg[0].dw[t] = (int8_t)(k == 3 ? t % 3 - 1 : 0);
       p.seg[0].dn[t] = 0;
     }
+    p.seg[0].patch = patch ? 1 : 0;
     p.B = B; p.H = H; p.W = W; p.Wp = Wp; p.Ktot = K; p.Cout = Cout; p.bias = bias;
     p.residual = residual; p.out = y_bf16;
     rc = tc_conv_plan_create(p, &plan);

@@ -137,6 +137,8 @@ struct TcConvSeg {
   int ntaps = 0;              // number of taps taken from this segment
   int8_t dh[9], dw[9];        // spatial shift of each tap (in this segment's grid)
   int dn[9];                  // batch-coordinate shift of each tap (plane select)
+  int patch = 0;              // a plain 3x3 window served from one halo patch per 64 channels; the
+                              // segment's weights are then K-ordered (64-channel block, tap, channel)
 };
 struct TcConvParams {
   TcConvSeg seg[3];
@@ -156,6 +158,8 @@ struct TcConvParams {
 };
 // fused statistics need a warp's 32 output rows inside one image
 bool tc_conv_stats_supported(int H, int W);
+// halo patches are available for this output grid (persistent kernel, H % 16 == 0, W % 8 == 0)
+bool tc_conv_patch_supported(int H, int W);
 // A prepared launch (tensor maps encoded once at plan time)
 struct TcConvPlan;
 int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out);

@@ -24,20 +24,13 @@
 #include "kernels.h"
 #include "tc_common.cuh"
 #include "tc_conv_epi.cuh"
+#include "tc_conv_plan.h"
 #include <cstdlib>
 #include <vector>
 
 namespace eo {
 
 namespace {
-
-struct KBlk { int seg; int c0; int dh_dw; int dn; };   // dh: low 16 bits, dw: high 16 bits
-
-struct TileGeom {
-  int bw, bh, bn;          // box extents, bw*bh*bn == 128
-  int tiles_w, tiles_h;
-  int H, W;
-};
 
 using tc::Epi;
 
@@ -222,20 +215,9 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   return EO_OK;
 }
 
-struct TcConvPlan {
-  CUtensorMap mapA[3];
-  CUtensorMap mapB;
-  KBlk* d_kblks = nullptr;
-  int nkb = 0;
-  TileGeom g{};
-  int bn_tile = 128;
-  bool pair = true;
-  TcConvParams p;
-};
-
 static long long* g_trace = nullptr;
 static int g_trace_n = 0;
-void tc_conv_set_trace(long long* dev_buf, int n_ctas) { g_trace = dev_buf; g_trace_n = n_ctas; }
+void tc_conv_set_trace(long long* dev_buf, int n_ctas) { g_trace = dev_buf; g_trace_n = n_ctas; tc_conv3_set_trace(dev_buf, n_ctas); }
 
 static int floor_pow2(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
 
@@ -256,6 +238,14 @@ int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out) {
   EO_REQUIRE(p.Cout % 64 == 0, EO_ERR_ARG, "tc_conv: Cout %d must be a multiple of 64", p.Cout);
   TcConvPlan* pl = new TcConvPlan();
   pl->p = p;
+  if (tc_conv3_enabled()) {
+    int rc3 = tc_conv3_plan_fill(p, pl);
+    if (rc3 != EO_OK) { tc_conv_plan_destroy(pl); return rc3; }
+    *out = pl;
+    return EO_OK;
+  }
+  for (int s = 0; s < p.nseg; ++s)
+    if (p.seg[s].patch) { delete pl; set_error("tc_conv: halo-patch weight order needs the persistent kernel"); return EO_ERR_ARG; }
   pl->pair = use_pairs();
   // ---- tile geometry: 128 pixels = bn x bh x bw
   TileGeom g;
@@ -364,6 +354,7 @@ static int launch_tc(const TcConvPlan* pl, int B, cudaStream_t st) {
 }
 
 int tc_conv_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
+  if (pl->v3) return tc_conv3_launch(pl, B, st);
   if (pl->pair) {
     // per CTA and stage: 16 KB of A + BN/2 weight rows (16 or 8 KB); two CTAs stay co-resident per SM
     if (pl->bn_tile == 256) return launch_tc<256, 3, true>(pl, B, st);
