@@ -294,6 +294,7 @@ struct eo_unet {
   template <typename T = void> T* ptr(size_t off) const { return reinterpret_cast<T*>(arena_base + off); }
 
   struct PackSeg { const float* wsrc; int cin_total; int ksize; int cin_off; int C; };
+  float* last_packed_bias = nullptr;   // bias vector of the conv planned last (plan_attn patches the qkv one)
 
   // SIMT layout [Ktot][Cout] fp32
   int pack_simt(const std::vector<PackSeg>& segs, int Cout, float** out, int* ktot, cudaStream_t st) {
@@ -476,6 +477,7 @@ struct eo_unet {
     if (rc) return rc;
     float* bias = nullptr;
     if (bias_a || bias_b) { rc = pack_bias2(bias_a, bias_b, Cout_rows, d_row_map, &bias, st); if (rc) return rc; }
+    last_packed_bias = bias;
     Act o = new_act(Cout_rows, Ho, Wo);
     if (want_stats && tc_conv_stats_supported(Ho, Wo)) {
       o.stats = (long long)ch_stats_floats;
@@ -634,12 +636,23 @@ struct eo_unet {
       rc = plan_conv_tc(p + "qkv", {seg1x1(xn)}, {{wq, C, 1, 0, C}}, rows, d_rmap, w(p + "qkv.bias"), nullptr, -1, nullptr,
                         x.H, x.W, &qkv, st, /*want_stats=*/false);
       if (rc) return rc;
+      // head dimension < 64: padded channel 63 of every head's v becomes 1.0 (zero weight row, bias 1), so the
+      // attention kernel gets the softmax row sums out of its P V product
+      const bool ones_col = ch < 64;
+      if (ones_col) {
+        float* qb = last_packed_bias;
+        const float one = 1.0f;
+        for (int h = 0; h < heads; ++h)
+          EO_CHECK_CUDA(cudaMemcpyAsync(qb + (h * 3 + 2) * 64 + 63, &one, sizeof(float), cudaMemcpyHostToDevice, st));
+        EO_CHECK_CUDA(cudaStreamSynchronize(st));   // `one` is a stack variable
+      }
       free_act(xn);
       Act a = new_act(C, x.H, x.W);
       const size_t ai = attn_plans.size();
       attn_plans.push_back(nullptr);
       auto prepare = [=]() -> int {
         TcAttnParams ap; ap.qkv = ptr(qkv.off); ap.out = ptr(a.off); ap.B = Bmax; ap.T = T; ap.heads = heads; ap.ch = ch;
+        ap.ones_col = ones_col ? 1 : 0;
         return tc_attn_plan_create(ap, &attn_plans[ai]);
       };
       push(p + "attention", [=](int B, cudaStream_t stx) -> int { return tc_attn_launch(attn_plans[ai], B, stx); }, 1, prepare);
@@ -1166,6 +1179,7 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
 
 int eo_debug_conv_trace(void* dev_buf, int n_ctas) {
   tc_conv_set_trace(reinterpret_cast<long long*>(dev_buf), n_ctas);
+  tc_attn_set_trace(reinterpret_cast<long long*>(dev_buf), n_ctas);
   return EO_OK;
 }
 
@@ -1184,12 +1198,24 @@ int eo_test_attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int
                                     reinterpret_cast<const __nv_bfloat16*>(qkv_bf16) + hp * ch, (size_t)ld_in * 2,
                                     (size_t)ch * 2, (size_t)B * T, cudaMemcpyDeviceToDevice, st));
   TcAttnParams p; p.qkv = padded; p.out = out_bf16; p.B = B; p.T = T; p.heads = heads; p.ch = ch;
+  __nv_bfloat16* ones = nullptr;
+  if (ch < 64) {   // channel 63 of every head's v = 1.0 (what the qkv convolution's bias does inside the UNet)
+    std::vector<__nv_bfloat16> h1((size_t)B * T, __float2bfloat16(1.0f));
+    EO_CHECK_CUDA(cudaMalloc(&ones, h1.size() * sizeof(__nv_bfloat16)));
+    EO_CHECK_CUDA(cudaMemcpyAsync(ones, h1.data(), h1.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice, st));
+    for (int hh = 0; hh < heads; ++hh)
+      EO_CHECK_CUDA(cudaMemcpy2DAsync(padded + (hh * 3 + 2) * 64 + 63, (size_t)ld * 2, ones, 2, 2, (size_t)B * T,
+                                      cudaMemcpyDeviceToDevice, st));
+    EO_CHECK_CUDA(cudaStreamSynchronize(st));
+    p.ones_col = 1;
+  }
   TcAttnPlan* plan = nullptr;
   rc = tc_attn_plan_create(p, &plan);
   if (!rc) rc = tc_attn_launch(plan, B, st);
   cudaError_t e = cudaStreamSynchronize(st);
   tc_attn_plan_destroy(plan);
   cudaFree(padded);
+  if (ones) cudaFree(ones);
   if (!rc && e != cudaSuccess) { set_error("eo_test_attention_tc: %s", cudaGetErrorString(e)); rc = EO_ERR_CUDA; }
   return rc;
 }

@@ -172,10 +172,12 @@ struct TcAttnParams {
   const void* qkv = nullptr;  // bf16 [B, T, heads*3*64]: per head q|k|v each padded to 64 channels
   void* out = nullptr;        // bf16 [B, T, heads*ch]
   int B = 0, T = 0, heads = 0, ch = 0;  // ch <= 64
+  int ones_col = 0;           // ch < 64 only: channel 63 of every head's v is 1.0, the kernel takes the softmax row sum from it
 };
 struct TcAttnPlan;
 int tc_attn_plan_create(const TcAttnParams& p, TcAttnPlan** out);
 void tc_attn_plan_destroy(TcAttnPlan* p);
 int tc_attn_launch(const TcAttnPlan* plan, int B, cudaStream_t st);
+void tc_attn_set_trace(long long* dev_buf, int n_ctas);   // development aid, see eo_debug_conv_trace
 
 }  // namespace eo

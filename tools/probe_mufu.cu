@@ -1,0 +1,54 @@
+// Hardware probe (development tool): MUFU.EX2 throughput per SM sub-partition with 1, 2, 4 warps per
+// scheduler, fp32 and fp16 variants, plus the same with FFMA/FADD work interleaved.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 tools/probe_mufu.cu -o tools/probe_mufu.bin
+#include <cstdio>
+#include <cuda_fp16.h>
+
+__device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ unsigned ex2h2(unsigned x) { unsigned y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+
+template <int MODE>
+__global__ void k(long long* out, float seed, int iters) {
+  float a[16];
+  for (int i = 0; i < 16; ++i) a[i] = seed + i * 0.001f + threadIdx.x * 1e-6f;
+  unsigned h[16];
+  for (int i = 0; i < 16; ++i) h[i] = __float_as_uint(a[i]) & 0x3bff3bffu;
+  float s0 = 0.f, s1 = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = ex2(a[i]);
+    } else if (MODE == 1) {      // + FFMA and FADD per element (the softmax inner loop)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { a[i] = ex2(fmaf(a[i], 0.999f, -0.001f)); s0 += a[i]; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) h[i] = ex2h2(h[i]);
+    }
+  }
+  const long long t1 = clock64();
+  for (int i = 0; i < 16; ++i) { s1 += a[i]; s1 += __uint_as_float(h[i]); }
+  if (s0 + s1 == 12345.f) out[1] = 1;
+  if (threadIdx.x == 0) out[0] = t1 - t0;
+}
+
+template <int MODE>
+void run(long long* d, int warps_per_smsp, const char* what, int per_iter) {
+  const int iters = 256;
+  k<MODE><<<1, 128 * warps_per_smsp>>>(d, 0.5f, iters);
+  cudaDeviceSynchronize();
+  long long h = 0;
+  cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  printf("%-28s %d warp(s) per scheduler: %6.2f clk per warp instruction per scheduler\n", what, warps_per_smsp,
+         (double)h / ((double)iters * per_iter * warps_per_smsp));
+}
+
+int main() {
+  long long* d; cudaMalloc(&d, 64);
+  for (int w : {1, 2, 4}) run<0>(d, w, "MUFU.EX2 f32", 16);
+  for (int w : {1, 2, 4}) run<1>(d, w, "FFMA + MUFU.EX2 + FADD", 16);
+  for (int w : {1, 2, 4}) run<2>(d, w, "ex2.f16x2 (2 MUFU.EX2.F16)", 16);
+  return 0;
+}
