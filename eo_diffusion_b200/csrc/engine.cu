@@ -437,7 +437,22 @@ struct eo_unet {
   }
 
   // bf16 tensor-core conv.  `tsegs` carry activation + taps; weights in `segs` (same order).
-  struct TcSegSpec { Act act; int batch_mult = 1; int ntaps = 9; int8_t dh[9]; int8_t dw[9]; int plane[9]; };
+  struct TcSegSpec {
+    Act act; int batch_mult = 1; int ntaps = 9; int8_t dh[9]; int8_t dw[9]; int plane[9];
+    bool has_gn = false; GnOut gn{}; int gn_coff = 0; int silu = 0;   // GroupNorm (+SiLU) folded into the operand load
+  };
+  static TcSegSpec with_gn(TcSegSpec s, const GnOut& g, int coff, int silu) {
+    s.has_gn = true; s.gn = g; s.gn_coff = coff; s.silu = silu;
+    return s;
+  }
+  // GroupNorm + SiLU can ride on the conv's operand load (persistent kernel; 3x3 windows need halo patches)
+  bool can_fuse_gn(int ksize, int Ho, int Wo, int C) const {
+    static int on = -1;
+    if (on < 0) { const char* e = std::getenv("EO_GN_FUSE"); on = (e && e[0] == '0') ? 0 : 1; }
+    if (!on || !tc_conv3_enabled() || C % 64 != 0) return false;
+    // a 1x1 conv would redo the transform for each of its N tiles (qkv: 6x) against one K block of MMA work
+    return ksize == 3 && tc_conv_patch_supported(Ho, Wo);
+  }
   static TcSegSpec seg3x3(const Act& a) {
     TcSegSpec s; s.act = a; s.ntaps = 9;
     for (int t = 0; t < 9; ++t) { s.dh[t] = (int8_t)(t / 3 - 1); s.dw[t] = (int8_t)(t % 3 - 1); s.plane[t] = 0; }
@@ -494,6 +509,10 @@ struct eo_unet {
       for (int i = 0; i < p.nseg; ++i) {
         p.seg[i].ptr = ptr(tv[i].act.off); p.seg[i].C = tv[i].act.C;
         p.seg[i].Bt = Bmax * tv[i].batch_mult; p.seg[i].ntaps = tv[i].ntaps; p.seg[i].patch = patch[i] ? 1 : 0;
+        if (tv[i].has_gn) {
+          p.seg[i].gn_scale = ptr<float>(tv[i].gn.scale_off); p.seg[i].gn_shift = ptr<float>(tv[i].gn.shift_off);
+          p.seg[i].gn_ld = tv[i].gn.C; p.seg[i].gn_coff = tv[i].gn_coff; p.seg[i].silu = tv[i].silu;
+        }
         for (int t = 0; t < tv[i].ntaps; ++t) {
           p.seg[i].dh[t] = tv[i].dh[t]; p.seg[i].dw[t] = tv[i].dw[t]; p.seg[i].dn[t] = tv[i].plane[t] * Bmax;
         }
@@ -563,18 +582,35 @@ struct eo_unet {
       free_gn(g2);
       free_act(h1);
     } else {
-      Act xn = plan_gn_apply(p + "in_layers.0", a, b, g1, 1);
-      free_gn(g1);
-      rc = plan_conv_tc(p + "in_layers.2", {seg3x3(xn)}, {{w1, L.cin, 3, 0, L.cin}}, L.cout, nullptr, nullptr, nullptr,
-                        L.tb_off, nullptr, a.H, a.W, &h1, st);
-      if (rc) return rc;
-      free_act(xn);
+      const bool fuse1 = can_fuse_gn(3, a.H, a.W, Ca) && (!b || Cb % 64 == 0);
+      if (fuse1) {
+        std::vector<TcSegSpec> ts; std::vector<PackSeg> sg;
+        ts.push_back(with_gn(seg3x3(a), g1, 0, 1)); sg.push_back({w1, L.cin, 3, 0, Ca});
+        if (b) { ts.push_back(with_gn(seg3x3(*b), g1, Ca, 1)); sg.push_back({w1, L.cin, 3, Ca, Cb}); }
+        rc = plan_conv_tc(p + "in_layers.2", ts, sg, L.cout, nullptr, nullptr, nullptr, L.tb_off, nullptr, a.H, a.W, &h1, st);
+        if (rc) return rc;
+        free_gn(g1);
+      } else {
+        Act xn = plan_gn_apply(p + "in_layers.0", a, b, g1, 1);
+        free_gn(g1);
+        rc = plan_conv_tc(p + "in_layers.2", {seg3x3(xn)}, {{w1, L.cin, 3, 0, L.cin}}, L.cout, nullptr, nullptr, nullptr,
+                          L.tb_off, nullptr, a.H, a.W, &h1, st);
+        if (rc) return rc;
+        free_act(xn);
+      }
       GnOut g2 = plan_gn(p + "out_layers.0", h1, nullptr, w(p + "out_layers.0.weight"), w(p + "out_layers.0.bias"));
-      Act hn = plan_gn_apply(p + "out_layers.0", h1, nullptr, g2, 1);
-      free_gn(g2);
-      free_act(h1);
+      const bool fuse2 = can_fuse_gn(3, a.H, a.W, L.cout);
+      Act hn;
       std::vector<TcSegSpec> ts; std::vector<PackSeg> sg;
-      ts.push_back(seg3x3(hn)); sg.push_back({w2, L.cout, 3, 0, L.cout});
+      if (fuse2) {
+        ts.push_back(with_gn(seg3x3(h1), g2, 0, 1));
+      } else {
+        hn = plan_gn_apply(p + "out_layers.0", h1, nullptr, g2, 1);
+        free_gn(g2);
+        free_act(h1);
+        ts.push_back(seg3x3(hn));
+      }
+      sg.push_back({w2, L.cout, 3, 0, L.cout});
       if (has_skip) {
         ts.push_back(seg1x1(a)); sg.push_back({wsk, L.cin, 1, 0, Ca});
         if (b) { ts.push_back(seg1x1(*b)); sg.push_back({wsk, L.cin, 1, Ca, Cb}); }
@@ -582,7 +618,7 @@ struct eo_unet {
       rc = plan_conv_tc(p + "out_layers.3", ts, sg, L.cout, nullptr, w(p + "out_layers.3.bias"),
                         has_skip ? w(p + "skip_connection.bias") : nullptr, -1, has_skip ? nullptr : &a, a.H, a.W, out, st);
       if (rc) return rc;
-      free_act(hn);
+      if (fuse2) { free_gn(g2); free_act(h1); } else free_act(hn);
     }
     return EO_OK;
   }
@@ -618,8 +654,9 @@ struct eo_unet {
         set_error("attention %s: head dimension %d unsupported in bf16 mode (multiple of 8, <= 64)", p.c_str(), ch);
         return EO_ERR_ARG;
       }
-      Act xn = plan_gn_apply(p + "norm", x, nullptr, g, 0);
-      free_gn(g);
+      const bool fuse = can_fuse_gn(1, x.H, x.W, C);
+      Act xn;
+      if (!fuse) { xn = plan_gn_apply(p + "norm", x, nullptr, g, 0); free_gn(g); }
       // qkv rows re-ordered to [head][q|k|v][64] with zero rows padding each part to 64
       const int rows = heads * 3 * 64;
       std::vector<int> rmap(rows, -1);
@@ -633,9 +670,10 @@ struct eo_unet {
       EO_CHECK_CUDA(cudaMemcpyAsync(d_rmap, rmap.data(), rows * sizeof(int), cudaMemcpyHostToDevice, st));
       EO_CHECK_CUDA(cudaStreamSynchronize(st));   // rmap is a stack-lifetime host buffer
       Act qkv;
-      rc = plan_conv_tc(p + "qkv", {seg1x1(xn)}, {{wq, C, 1, 0, C}}, rows, d_rmap, w(p + "qkv.bias"), nullptr, -1, nullptr,
-                        x.H, x.W, &qkv, st, /*want_stats=*/false);
+      rc = plan_conv_tc(p + "qkv", {fuse ? with_gn(seg1x1(x), g, 0, 0) : seg1x1(xn)}, {{wq, C, 1, 0, C}}, rows, d_rmap,
+                        w(p + "qkv.bias"), nullptr, -1, nullptr, x.H, x.W, &qkv, st, /*want_stats=*/false);
       if (rc) return rc;
+      if (fuse) free_gn(g);
       // head dimension < 64: padded channel 63 of every head's v becomes 1.0 (zero weight row, bias 1), so the
       // attention kernel gets the softmax row sums out of its P V product
       const bool ones_col = ch < 64;
@@ -646,7 +684,7 @@ struct eo_unet {
           EO_CHECK_CUDA(cudaMemcpyAsync(qb + (h * 3 + 2) * 64 + 63, &one, sizeof(float), cudaMemcpyHostToDevice, st));
         EO_CHECK_CUDA(cudaStreamSynchronize(st));   // `one` is a stack variable
       }
-      free_act(xn);
+      if (!fuse) free_act(xn);
       Act a = new_act(C, x.H, x.W);
       const size_t ai = attn_plans.size();
       attn_plans.push_back(nullptr);
@@ -1155,6 +1193,7 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
     rc = launch_pack_conv_weight(w, Cin, k, 0, Cin, Wp, DT_BF16, K, 1, 0, Cout, nullptr, st);
   }
   TcConvPlan* plan = nullptr;
+  float* gn_buf = nullptr;
   if (!rc) {
     TcConvParams p;
     p.nseg = 1;
@@ -1165,6 +1204,18 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
       p.seg[0].dn[t] = 0;
     }
     p.seg[0].patch = patch ? 1 : 0;
+    // development aid (tools/conv_check.py): EO_TEST_GN=1 folds an identity GroupNorm affine (scale 1,
+    // shift 0) into the operand load, =2 adds the SiLU (the caller then compares against conv(silu(x)))
+    const char* tg = std::getenv("EO_TEST_GN");
+    if (tg && (tg[0] == '1' || tg[0] == '2') && tc_conv3_enabled() && patch) {
+      std::vector<float> ones((size_t)B * Cin, 1.0f);
+      EO_CHECK_CUDA(cudaMalloc(&gn_buf, 2 * ones.size() * sizeof(float)));
+      EO_CHECK_CUDA(cudaMemsetAsync(gn_buf, 0, 2 * ones.size() * sizeof(float), st));
+      EO_CHECK_CUDA(cudaMemcpyAsync(gn_buf, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+      EO_CHECK_CUDA(cudaStreamSynchronize(st));
+      p.seg[0].gn_scale = gn_buf; p.seg[0].gn_shift = gn_buf + ones.size(); p.seg[0].gn_ld = Cin;
+      p.seg[0].silu = tg[0] == '2';
+    }
     p.B = B; p.H = H; p.W = W; p.Wp = Wp; p.Ktot = K; p.Cout = Cout; p.bias = bias;
     p.residual = residual; p.out = y_bf16;
     rc = tc_conv_plan_create(p, &plan);
@@ -1173,6 +1224,7 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
   cudaError_t e = cudaStreamSynchronize(st);
   tc_conv_plan_destroy(plan);
   cudaFree(Wp);
+  if (gn_buf) cudaFree(gn_buf);
   if (!rc && e != cudaSuccess) { set_error("eo_test_conv_tc: %s", cudaGetErrorString(e)); rc = EO_ERR_CUDA; }
   return rc;
 }

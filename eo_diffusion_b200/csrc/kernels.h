@@ -137,6 +137,11 @@ struct TcConvSeg {
   int ntaps = 0;              // number of taps taken from this segment
   int8_t dh[9], dw[9];        // spatial shift of each tap (in this segment's grid)
   int dn[9];                  // batch-coordinate shift of each tap (plane select)
+  // GroupNorm (+ SiLU) of this segment folded into the operand load (persistent kernel only; a 3x3
+  // segment must then be a patch segment): act(x * gn_scale[b, gn_coff + c] + gn_shift[b, gn_coff + c])
+  const float* gn_scale = nullptr;   // [B, gn_ld]
+  const float* gn_shift = nullptr;
+  int gn_ld = 0, gn_coff = 0, silu = 0;
   int patch = 0;              // a plain 3x3 window served from one halo patch per 64 channels; the
                               // segment's weights are then K-ordered (64-channel block, tap, channel)
 };
@@ -160,6 +165,8 @@ struct TcConvParams {
 bool tc_conv_stats_supported(int H, int W);
 // halo patches are available for this output grid (persistent kernel, H % 16 == 0, W % 8 == 0)
 bool tc_conv_patch_supported(int H, int W);
+// the persistent kernel (tc_conv3.cu) is in use (EO_CONV_V2=1 selects the one-tile-per-CTA kernel instead)
+bool tc_conv3_enabled();
 // A prepared launch (tensor maps encoded once at plan time)
 struct TcConvPlan;
 int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out);

@@ -166,6 +166,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
+// remote arrival with the default .release.cta semantics (what CUTLASS's ClusterBarrier::arrive(cta_id) emits):
+// a MEMBAR at CTA scope in front of it, not the GPU-scope one of .release.cluster, which also waits for
+// every global load the thread has in flight.  Shared-memory writes handed to the async proxy are ordered
+// by fence.proxy.async before it.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
 // TMA loads issued by either CTA of a pair, completing on a barrier of the leader CTA
 __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
                                              int c0, int c1) {

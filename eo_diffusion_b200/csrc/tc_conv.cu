@@ -245,7 +245,11 @@ int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out) {
     return EO_OK;
   }
   for (int s = 0; s < p.nseg; ++s)
-    if (p.seg[s].patch) { delete pl; set_error("tc_conv: halo-patch weight order needs the persistent kernel"); return EO_ERR_ARG; }
+    if (p.seg[s].patch || p.seg[s].gn_scale) {
+      delete pl;
+      set_error("tc_conv: halo patches and folded GroupNorm need the persistent kernel");
+      return EO_ERR_ARG;
+    }
   pl->pair = use_pairs();
   // ---- tile geometry: 128 pixels = bn x bh x bw
   TileGeom g;

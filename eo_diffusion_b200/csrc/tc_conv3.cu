@@ -20,14 +20,25 @@
 //     swizzle is a function of the absolute address, tools/probe_shifted_desc.cu), cutting the
 //     activation traffic L2 -> SM from 9 x 16 KB to 22.5 KB per 64 channels.
 //
-// Warp roles (352 threads): 0 = operand producer (TMA), 1 = TMEM owner + MMA issuer, 2..9 =
-// epilogue (two sets of four, TMEM lane quadrant warp % 4), 10 = residual producer.
+//   * GroupNorm + SiLU of the operand folded in: for such a segment the halo patch is not fetched by
+//     TMA; four transform warps load it from global memory into registers, apply
+//     act(x * scale[n,c] + shift[n,c]) and write the 128B-swizzled operand stage themselves (zeros for
+//     halo pixels outside the image: the convolution pads the NORMALISED activation).  One pass through
+//     the shared-memory port, like the TMA write it replaces -- a first version that let TMA land the
+//     raw patch and rewrote it in place tripled the patch's shared-memory traffic against a port the
+//     MMA operand reads already saturate, and lost more than the separate bandwidth pass
+//     (k_gn_apply: 10.7 ms of an 85 ms step) it was meant to remove.  A patch is transformed once for
+//     its nine taps.
+//
+// Warp roles (640 threads, registers redistributed with setmaxnreg): 0 = operand producer (TMA), 1 = TMEM owner + MMA issuer, 2 = residual
+// producer, 4..11 = epilogue (two sets of four, TMEM lane quadrant warp % 4), 12..19 = transform.
 //
 // Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2 * M * Cout * Ktot.
 #include "kernels.h"
 #include "tc_common.cuh"
 #include "tc_conv_plan.h"
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 namespace eo {
@@ -40,24 +51,27 @@ constexpr int PATCH_W = 10, PATCH_H = 18;                  // halo patch of an 8
 constexpr int PATCH_BYTES = PATCH_W * PATCH_H * 128;       // 23040
 constexpr int PLAIN_BYTES = BM * 128;                      // 16384
 constexpr int A_STAGE = 23552;                             // 23 KB: PATCH_BYTES rounded up to 1 KB
-constexpr int SA = 3;                                      // operand-A stages
+constexpr int SA_MAX = 4;                                  // operand-A stages: SAR filled by TMA + SAG by the transform warps
 constexpr int STG_BYTES = BM * 128;                        // one 128-row x 64-channel bf16 tile
 constexpr int MAX_ENT = 176;
 constexpr int MAX_SB = 12;
 constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;
 constexpr int SMEM_LIMIT = 232448;                         // 227 KB per CTA
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 32 * (3 + NUM_EPI_WARPS);   // producer, MMA, 8 epilogue, residual producer
+constexpr int EPI_WARP0 = 4, XF_WARP0 = 12, XF_WARPS = 8;   // first epilogue warp, first transform warp
+constexpr int NUM_THREADS = 32 * (XF_WARP0 + XF_WARPS);     // producer, MMA, residual producer, (spare), 8 epilogue, 8 transform
+constexpr int XF_PIX = (PATCH_W * PATCH_H + 4 * XF_WARPS - 1) / (4 * XF_WARPS);   // patch pixels per transform thread (6)
 
-// fixed part of the shared-memory layout (offsets from the 1 KB-aligned base); the B ring follows
+// shared-memory layout after the nA operand-A stages (offsets from nA * A_STAGE past the 1 KB-aligned
+// base); the B ring follows
 struct Smem {
-  static constexpr int A_OFF = 0;
-  static constexpr int STG_OFF = A_OFF + SA * A_STAGE;                 // 2 staging tiles
+  static constexpr int STG_OFF = 0;                                    // 2 staging tiles
   static constexpr int TAB_OFF = STG_OFF + 2 * STG_BYTES;
   static constexpr int STAT_OFF = TAB_OFF + MAX_ENT * (int)sizeof(KEnt3);   // [4 warps][256][2] floats
   static constexpr int BAR_OFF = STAT_OFF + 4 * 256 * 2 * 4;
-  // a_full[SA] a_empty[SA] b_full[MAX_SB] b_empty[MAX_SB] tmem_full[2] tmem_empty[2] res_full[2] res_empty[2]
-  static constexpr int NBAR = 2 * SA + 2 * MAX_SB + 8;
+  // r_full r_empty g_ready g_empty [SA_MAX each] b_full[MAX_SB] b_empty[MAX_SB] tmem_full[2] tmem_empty[2]
+  // res_full[2] res_empty[2]
+  static constexpr int NBAR = 4 * SA_MAX + 2 * MAX_SB + 8;
   static constexpr int VAR_OFF = (BAR_OFF + NBAR * 8 + 16 + 1023) & ~1023;  // residual tiles (optional), then B ring
 };
 
@@ -102,7 +116,7 @@ __device__ __forceinline__ float warp_column_sums(float (&f)[32], int lane) {
 
 // development aid (eo_debug_conv_trace, TRACE instantiation only): per-CTA counters, slot = 0 lifetime,
 // 1 MMA waits on operands, 2 MMA waits on a free accumulator, 3 epilogue waits on the accumulator,
-// 4 epilogue busy, 5 producer waits on free stages, 6 tiles, 7 SM id (clock64 ticks)
+// 4 epilogue busy, 5 producer waits on free stages, 6 tiles, 7 transform warps busy (clock64 ticks)
 __device__ __forceinline__ void trace_put(const Epi3& ep, int slot, long long v) {
   if (ep.trace && (int)blockIdx.x < ep.trace_n) ep.trace[(long long)blockIdx.x * 8 + slot] = v;
 }
@@ -120,15 +134,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
            const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
            const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
-           const KEnt3* __restrict__ ents, int nent, Geom3 g, int B, int BN, int SB, int n_work, int n_ntiles,
-           Epi3 ep) {
+           const KEnt3* __restrict__ ents, int nent, Geom3 g, int B, int BN, int SB, int SAR, int SAG, int n_work,
+           int n_ntiles, Epi3 ep) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
+  uint8_t* smem_a = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);   // operand-A stages
+  uint8_t* smem = smem_a + (SAR + SAG) * A_STAGE;                                    // everything else
+  uint8_t* smem_g = smem_a + SAR * A_STAGE;                                          // the transform warps' stages
   KEnt3* tab = reinterpret_cast<KEnt3*>(smem + Smem::TAB_OFF);
   float* sstat = reinterpret_cast<float*>(smem + Smem::STAT_OFF);
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Smem::BAR_OFF);
-  uint64_t* a_empty = a_full + SA;
-  uint64_t* b_full = a_empty + SA;
+  // Operand A has two rings, one per filler, so that nobody has to track a stage it does not fill: stages
+  // loaded by TMA as is (both CTAs' bytes complete on the leader's r_full), and stages the transform warps
+  // write with GroupNorm folded in (both CTAs' warps arrive on the leader's g_ready).
+  uint64_t* r_full = reinterpret_cast<uint64_t*>(smem + Smem::BAR_OFF);
+  uint64_t* r_empty = r_full + SA_MAX;
+  uint64_t* g_ready = r_empty + SA_MAX;
+  uint64_t* g_empty = g_ready + SA_MAX;
+  uint64_t* b_full = g_empty + SA_MAX;
   uint64_t* b_empty = b_full + MAX_SB;
   uint64_t* tmem_full = b_empty + MAX_SB;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -150,7 +171,10 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     tc::tma_prefetch_desc(&mapA0);
     tc::tma_prefetch_desc(&mapB);
     tc::tma_prefetch_desc(&mapOut);
-    for (int s = 0; s < SA; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SA_MAX; ++s) {
+      tc::mbar_init(&r_full[s], 1); tc::mbar_init(&r_empty[s], 1);
+      tc::mbar_init(&g_ready[s], 2 * XF_WARPS); tc::mbar_init(&g_empty[s], 1);
+    }
     for (int s = 0; s < MAX_SB; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&tmem_full[s], 1);
@@ -167,36 +191,45 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // 640 threads leave 96 registers each (61440 for the CTA); the epilogue warps need more and the issue
+  // warps far fewer: warpgroup 0 drops to 40, the transform warpgroups to 88, the epilogue warpgroups
+  // grow to 128 (40 + 2*128 + 2*88 = 472 <= 480 = 5 * 96: setmaxnreg.inc can always be satisfied)
+
   // Producer and MMA warps: the WHOLE warp walks the loops (warp-uniform control flow keeps addresses,
   // coordinates and descriptors in uniform registers) and one elected lane issues.  Under
   // `if (lane == 0)` ptxas wraps every TMA / MMA instruction in a read-lane loop and the issuing
   // thread, not the tensor pipe, becomes the limiter (measured: 650 clk per 64-deep K block).
   if (warp == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // ------------------------------------------------------------------ operand producer
     Ring ra, rb;
     long long tr_wait = 0;
-    const uint32_t a_full_l = tc::mapa_u32(tc::smem_u32(&a_full[0]), 0);   // the leader's barriers
+    const uint32_t r_full_l = tc::mapa_u32(tc::smem_u32(&r_full[0]), 0);   // the leader's barriers
     const uint32_t b_full_l = tc::mapa_u32(tc::smem_u32(&b_full[0]), 0);
     const int b_row = (int)rank * (BN / 2);
     for (int w = cid; w < n_work; w += ncl) {
       const Tile t = decode_tile(w, n_ntiles, rank, g, BN);
       for (int e = 0; e < nent; ++e) {
         const KEnt3 en = tab[e];
-        { TRACE_T0(); tc::mbar_wait(&a_empty[ra.i], ra.ph ^ 1); TRACE_ACC(tr_wait); }
+        if (!en.gn) { TRACE_T0(); tc::mbar_wait(&r_empty[ra.i], ra.ph ^ 1); TRACE_ACC(tr_wait); }
         const CUtensorMap* ma = en.seg == 0 ? &mapA0 : (en.seg == 1 ? &mapA1 : &mapA2);
-        if (tc::elect_one()) {
-          // One arrival per phase: the leader's producer, which posts the byte count of BOTH CTAs'
-          // loads; the peer's TMA only completes transactions on the leader's barrier.
-          if (rank == 0) tc::mbar_arrive_expect_tx(&a_full[ra.i], 2 * (en.patch ? PATCH_BYTES : PLAIN_BYTES));
-          tc::tma2_load_4d(smem + Smem::A_OFF + ra.i * A_STAGE, ma, a_full_l + ra.i * 8, en.c0,
-                           t.w0 + (en.patch ? -1 : en.dw), t.h0 + (en.patch ? -1 : en.dh), t.n0 + en.dn);
+        if (!en.gn && tc::elect_one()) {
+          const int dh = (int)(short)(en.dhw & 0xffff), dw = en.dhw >> 16;
+          const int cw = t.w0 + (en.patch ? -1 : dw), chh = t.h0 + (en.patch ? -1 : dh);
+          const uint32_t bytes = en.patch ? PATCH_BYTES : PLAIN_BYTES;
+          uint8_t* dst = smem_a + ra.i * A_STAGE;
+          // one arrival per phase: the leader's producer, which posts the byte count of BOTH CTAs' loads
+          if (rank == 0) tc::mbar_arrive_expect_tx(&r_full[ra.i], 2 * bytes);
+          tc::tma2_load_4d(dst, ma, r_full_l + ra.i * 8, en.c0, cw, chh, t.n0 + en.dn);
         }
         __syncwarp();
-        ra.next(SA);
+        if (!en.gn) ra.next((uint32_t)SAR);
         const int nb = en.patch ? 9 : 1;
         for (int j = 0; j < nb; ++j) {
           { TRACE_T0(); tc::mbar_wait(&b_empty[rb.i], rb.ph ^ 1); TRACE_ACC(tr_wait); }
           if (tc::elect_one()) {
+            // one arrival per phase: the leader's producer, which posts the byte count of BOTH CTAs'
+            // loads; the peer's TMA only completes transactions on the leader's barrier
             if (rank == 0) tc::mbar_arrive_expect_tx(&b_full[rb.i], 2 * b_bytes);
             tc::tma2_load_2d(b_sm + rb.i * b_bytes, &mapB, b_full_l + rb.i * 8, en.kofs + j * BK, t.nbase + b_row);
           }
@@ -207,12 +240,13 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     }
     if (TRACE && lane == 0) trace_put(ep, 5, tr_wait);
   } else if (warp == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // ------------------------------------------------------------------ MMA issuer (leader CTA)
     if (rank == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(2 * BM, BN, 0, 0);
       const uint64_t bdesc0 = tc::make_sw128_desc(tc::smem_u32(b_sm));
       const uint32_t b_step = (uint32_t)b_bytes >> 4;
-      Ring ra, rb;
+      Ring ra, rg, rb;
       uint32_t it = 0;
       long long tr_ops = 0, tr_acc = 0;
       for (int w = cid; w < n_work; w += ncl, ++it) {
@@ -223,9 +257,16 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         uint32_t acc = 0;
         for (int e = 0; e < nent; ++e) {
           const int patch = tab[e].patch;
-          { TRACE_T0(); tc::mbar_wait(&a_full[ra.i], ra.ph); TRACE_ACC(tr_ops); }
+          const bool gn = tab[e].gn != 0;
+          {
+            TRACE_T0();
+            if (gn) tc::mbar_wait_cluster(&g_ready[rg.i], rg.ph);
+            else tc::mbar_wait(&r_full[ra.i], ra.ph);
+            TRACE_ACC(tr_ops);
+          }
           tc::tc_fence_after();
-          const uint32_t a_base = tc::smem_u32(smem + Smem::A_OFF + ra.i * A_STAGE);
+          const uint32_t a_base = tc::smem_u32(gn ? smem_g + rg.i * A_STAGE : smem_a + ra.i * A_STAGE);
+          uint64_t* a_release = gn ? &g_empty[rg.i] : &r_empty[ra.i];
           const bool last_e = e == nent - 1;
           // one weight tile: wait for it, issue the 4 K=16 MMAs of this 64-deep K block, release it
           auto kblock = [&](uint64_t adesc, bool last_of_a) {
@@ -238,7 +279,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 tc::umma2_f16_ss(d_tmem, tc::desc_advance(adesc, k * 32), tc::desc_advance(bdesc, k * 32), idesc,
                                  k ? 1u : acc);
               tc::umma2_commit_mc(&b_empty[rb.i], 3);                   // frees the weight stage in both CTAs
-              if (last_of_a) tc::umma2_commit_mc(&a_empty[ra.i], 3);    // ... and the activation stage
+              if (last_of_a) tc::umma2_commit_mc(a_release, 3);          // ... and the activation stage
               if (last_of_a && last_e) tc::umma2_commit_mc(&tmem_full[ab], 3);   // accumulator complete
             }
             __syncwarp();
@@ -254,23 +295,24 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           } else {
             kblock(tc::make_sw128_desc(a_base), true);
           }
-          ra.next(SA);
+          if (gn) rg.next((uint32_t)SAG); else ra.next((uint32_t)SAR);
         }
       }
       if (TRACE && lane == 0) { trace_put(ep, 1, tr_ops); trace_put(ep, 2, tr_acc); trace_put(ep, 6, it); }
     }
-  } else if (warp == 2 + NUM_EPI_WARPS) {
-    // ------------------------------------------------------------------ residual producer
-    if (has_res) {
+  } else if (warp == 2 || warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    // ------------------------------------------------------------------ residual producer (warp 3 idles)
+    if (has_res && warp == 2) {
       if (lane == 0) tc::tma_prefetch_desc(&mapRes);
-      uint32_t uses[2] = {0, 0};
+      uint32_t uses0 = 0, uses1 = 0;
       const int nchunks = BN / 64;
       for (int w = cid; w < n_work; w += ncl) {
         const Tile t = decode_tile(w, n_ntiles, rank, g, BN);
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t rbuf = c & 1;                  // chunk c belongs to epilogue set c & 1
-          tc::mbar_wait(&res_empty[rbuf], (uses[rbuf] & 1) ^ 1);
-          ++uses[rbuf];
+          tc::mbar_wait(&res_empty[rbuf], ((rbuf ? uses1 : uses0) & 1) ^ 1);
+          if (rbuf) ++uses1; else ++uses0;
           if (tc::elect_one()) {
             tc::mbar_arrive_expect_tx(&res_full[rbuf], STG_BYTES);
             tc::tma_load_4d(res_sm + rbuf * STG_BYTES, &mapRes, &res_full[rbuf], t.nbase + c * 64, t.w0, t.h0, t.n0);
@@ -279,13 +321,168 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         }
       }
     }
-  } else {
+  } else if (warp >= XF_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    // ------------------------------------------------------------------ operand transform
+    // GroupNorm affine (+ SiLU) of the activation, applied in place to the stage TMA just filled
+    // (reference: normalization / nn.SiLU in front of every conv, unet_openai.py:313-316, :337-342,
+    // :411-412; same arithmetic as k_gn_apply: fp32 x*scale+shift, tanh-form SiLU, round to bf16).
+    // Thread <-> one 16-byte chunk (8 channels) of every 16th pixel; the 128B swizzle TMA applied
+    // (chunk ^ pixel & 7) is undone in the address.  Pixels of a halo patch that lie outside the image
+    // stay zero: the convolution pads the NORMALISED activation with zeros.
+    const int xt = threadIdx.x - XF_WARP0 * 32;        // 0..255
+    const int ch8 = xt & 7, pl = xt >> 3;              // channel chunk, pixel lane (0..31)
+    const uint32_t g_ready_l = tc::mapa_u32(tc::smem_u32(&g_ready[0]), 0);
+    // the thread's 6 pixels q = pl + 32 i of a patch never change: byte offset of its 16-byte chunk in the
+    // (swizzled) stage in the low 16 bits, the patch borders the pixel lies on in bits 16.. (top, bottom,
+    // left, right; bit 20 = beyond the patch); plin = pixel offset inside the image relative to the
+    // patch origin
+    uint32_t ptab[XF_PIX];
+    int plin[XF_PIX];
+#pragma unroll
+    for (int i = 0; i < XF_PIX; ++i) {
+      const int q = pl + 4 * XF_WARPS * i;
+      const int ph = q / PATCH_W, pw = q - ph * PATCH_W;
+      uint32_t edge = (ph == 0 ? 1u : 0u) | (ph == PATCH_H - 1 ? 2u : 0u) | (pw == 0 ? 4u : 0u) | (pw == PATCH_W - 1 ? 8u : 0u);
+      if (q >= PATCH_W * PATCH_H) edge = 16u;
+      ptab[i] = (uint32_t)(q * 128 + ((ch8 ^ (q & 7)) << 4)) | (edge << 16);
+      plin[i] = ph * g.W + pw;
+    }
+    // cursor over the GroupNorm-folded operand loads of this CTA, in the order the MMA warp consumes them
+    struct Cur { int w, e; Ring ring; Tile t; bool valid; };
+    auto seek = [&](Cur& c, bool first) {      // advance to the next such load (or the first one)
+      for (;;) {
+        if (!first) {
+          if (tab[c.e].gn) c.ring.next((uint32_t)SAG);
+          if (++c.e == nent) { c.e = 0; c.w += ncl; }
+        }
+        first = false;
+        if (c.w >= n_work) { c.valid = false; return; }
+        if (c.e == 0) c.t = decode_tile(c.w, n_ntiles, rank, g, BN);
+        if (tab[c.e].gn) { c.valid = true; return; }
+      }
+    };
+    // one patch = 6 x 16 bytes per thread in registers
+    uint4 buf[XF_PIX];
+    float4 na0, na1, nb0, nb1;                 // scale / shift of the next patch
+    na0 = na1 = nb0 = nb1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto edges_of = [&](const Tile& t) -> uint32_t {   // image borders the tile touches (+ "beyond the patch")
+      return ((t.h0 == 0 ? 1u : 0u) | (t.h0 + 16 == g.H ? 2u : 0u) | (t.w0 == 0 ? 4u : 0u) | (t.w0 + 8 == g.W ? 8u : 0u) | 16u) << 16;
+    };
+    auto src_of = [&](const Cur& c, const KEnt3& en, int& Cs) -> const uint8_t* {
+      // (constant-index selects: a dynamically indexed kernel parameter array is copied to local memory)
+      const void* sp = en.seg == 0 ? ep.gn_src[0] : (en.seg == 1 ? ep.gn_src[1] : ep.gn_src[2]);
+      Cs = en.seg == 0 ? ep.gn_C[0] : (en.seg == 1 ? ep.gn_C[1] : ep.gn_C[2]);
+      const long long pix0 = ((long long)c.t.n0 * g.H + (c.t.h0 - 1)) * g.W + (c.t.w0 - 1);
+      return reinterpret_cast<const uint8_t*>(sp) + (pix0 * Cs + en.c0 + ch8 * 8) * 2;
+    };
+    auto load_affine = [&](const Cur& c, const KEnt3& en) {
+      if (c.t.n0 >= B) return;
+      const float* gsc = en.seg == 0 ? ep.gn_scale[0] : (en.seg == 1 ? ep.gn_scale[1] : ep.gn_scale[2]);
+      const float* gsh = en.seg == 0 ? ep.gn_shift[0] : (en.seg == 1 ? ep.gn_shift[1] : ep.gn_shift[2]);
+      const int gld = en.seg == 0 ? ep.gn_ld[0] : (en.seg == 1 ? ep.gn_ld[1] : ep.gn_ld[2]);
+      const long long o = (long long)c.t.n0 * gld + en.gnc + ch8 * 8;
+      na0 = __ldg(reinterpret_cast<const float4*>(gsc + o));
+      na1 = __ldg(reinterpret_cast<const float4*>(gsc + o + 4));
+      nb0 = __ldg(reinterpret_cast<const float4*>(gsh + o));
+      nb1 = __ldg(reinterpret_cast<const float4*>(gsh + o + 4));
+    };
+    Cur cur{cid, 0, Ring(), Tile(), false};
+    seek(cur, true);
+    if (cur.valid) {
+      const KEnt3 en = tab[cur.e];
+      int Cs;
+      const uint8_t* src = src_of(cur, en, Cs);
+      const uint32_t te = cur.t.n0 < B ? edges_of(cur.t) : 0xffffffffu;
+      load_affine(cur, en);
+#pragma unroll
+      for (int i = 0; i < XF_PIX; ++i)
+        if (!(ptab[i] & te)) buf[i] = __ldg(reinterpret_cast<const uint4*>(src + (long long)plin[i] * Cs * 2));
+    }
+    long long tr_xb = 0;
+    while (cur.valid) {
+      const KEnt3 en = tab[cur.e];
+      const bool silu = en.gn == 2;
+      const uint32_t te = cur.t.n0 < B ? edges_of(cur.t) : 0xffffffffu;
+      // scale / shift of this thread's 8 channels.  With SiLU they are halved: silu(y) = h + h tanh(h),
+      // h = y/2 (common.cuh silu_f), and 0.5 * fma(x, s, b) == fma(x, 0.5 s, 0.5 b) exactly.
+      const float hf = silu ? 0.5f : 1.0f;
+      const float4 a0 = make_float4(na0.x * hf, na0.y * hf, na0.z * hf, na0.w * hf);
+      const float4 a1 = make_float4(na1.x * hf, na1.y * hf, na1.z * hf, na1.w * hf);
+      const float4 b0 = make_float4(nb0.x * hf, nb0.y * hf, nb0.z * hf, nb0.w * hf);
+      const float4 b1 = make_float4(nb1.x * hf, nb1.y * hf, nb1.z * hf, nb1.w * hf);
+      Cur nxt = cur;
+      seek(nxt, false);
+      KEnt3 en2 = en;
+      int Cs2 = 0;
+      const uint8_t* src2 = nullptr;
+      uint32_t te2 = 0xffffffffu;
+      if (nxt.valid) {
+        en2 = tab[nxt.e];
+        src2 = src_of(nxt, en2, Cs2);
+        if (nxt.t.n0 < B) te2 = edges_of(nxt.t);
+      }
+      tc::mbar_wait(&g_empty[cur.ring.i], cur.ring.ph ^ 1);       // the MMAs that read this stage have retired
+      const long long t_b0 = TRACE ? clock64() : 0;
+      uint8_t* st = smem_g + cur.ring.i * A_STAGE;
+      // one bf16 pair: affine (+ SiLU) in fp32, back to bf16
+      auto xf2 = [&](uint32_t in, float s0, float h0, float s1, float h1, bool act) -> uint32_t {
+        float x0 = __uint_as_float(in << 16), x1 = __uint_as_float(in & 0xffff0000u);
+        x0 = fmaf(x0, s0, h0);
+        x1 = fmaf(x1, s1, h1);
+        if (act) {
+          float t0, t1;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(x0));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(x1));
+          x0 = fmaf(x0, t0, x0);
+          x1 = fmaf(x1, t1, x1);
+        }
+        __nv_bfloat162 o = __floats2bfloat162_rn(x0, x1);
+        return *reinterpret_cast<uint32_t*>(&o);
+      };
+      auto run = [&](auto act_tag) {
+        constexpr bool ACT = decltype(act_tag)::value;
+#pragma unroll
+        for (int i = 0; i < XF_PIX; ++i) {
+          if (ptab[i] & (16u << 16)) continue;                    // beyond the patch (only the last i)
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          const bool in_img = !(ptab[i] & te);
+          if (in_img) v = buf[i];
+          if (in_img) {
+            v.x = xf2(v.x, a0.x, b0.x, a0.y, b0.y, ACT);
+            v.y = xf2(v.y, a0.z, b0.z, a0.w, b0.w, ACT);
+            v.z = xf2(v.z, a1.x, b1.x, a1.y, b1.y, ACT);
+            v.w = xf2(v.w, a1.z, b1.z, a1.w, b1.w, ACT);
+          }
+          *reinterpret_cast<uint4*>(st + (ptab[i] & 0xffffu)) = v;    // zeros outside the image
+        }
+      };
+      if (silu) run(std::true_type{}); else run(std::false_type{});
+      tc::fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's operand reads
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_remote(g_ready_l + cur.ring.i * 8);
+      if (TRACE) tr_xb += clock64() - t_b0;
+      // the next patch's loads go out only now: a fence waits for every load the thread has in flight, so
+      // loads issued before it would serialise on their own latency.  They arrive while this thread waits
+      // for the MMA warp to release the next stage (it runs up to two stages ahead of the tensor pipe).
+      if (nxt.valid) {
+        load_affine(nxt, en2);
+#pragma unroll
+        for (int i = 0; i < XF_PIX; ++i)
+          if (!(ptab[i] & te2)) buf[i] = __ldg(reinterpret_cast<const uint4*>(src2 + (long long)plin[i] * Cs2 * 2));
+      }
+      cur = nxt;
+    }
+    if (TRACE && xt == 0) trace_put(ep, 7, tr_xb);
+#undef EO_LOAD_AFFINE
+  } else if (warp >= EPI_WARP0) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     // ------------------------------------------------------------------ epilogue
     // Two sets of four warps (one warp per TMEM lane quadrant in each); set s takes the 64-channel
     // chunks c = s, s+2, ... of every tile.  A warp owns 32 accumulator rows end to end: TMEM ->
     // registers -> its 4 KB slice of the staging tile -> its own TMA store (a 32-pixel sub-box), so
     // the only cross-warp synchronisation is the per-tile combine of the GroupNorm sums.
-    const int ew = warp - 2;                       // 0..7
+    const int ew = warp - EPI_WARP0;               // 0..7
     const int set = ew >> 2;
     const int q = warp & 3;                        // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
@@ -323,15 +520,6 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
 #pragma unroll 1
       for (int c = set; c < nchunks; c += 2) {
         const uint32_t taddr = tmem_base + ab * ACC_STRIDE + (uint32_t)(c * 64) + ((uint32_t)(q * 32) << 16);
-        uint32_t v[2][32];
-        tc::tmem_ld_32x32(taddr, v[0]);
-        tc::tmem_ld_32x32(taddr + 32, v[1]);
-        tc::tmem_ld_wait();
-        if (c + 2 >= nchunks) {                    // this warp's share of the accumulator now lives in registers
-          tc::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive_cluster_relaxed(tmem_empty_leader + ab * 8);
-        }
         if (has_res) { tc::mbar_wait(&res_full[set], res_uses & 1); ++res_uses; }
         // the TMA store this warp issued from its staging rows one chunk ago has read them out
         if (lane == 0) bulk_wait_read0();      // (bulk groups belong to the issuing thread: always lane 0)
@@ -340,8 +528,18 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         for (int half = 0; half < 2; ++half) {
           const int n = t.nbase + c * 64 + half * 32;
           float f[32];
+          {
+            uint32_t v[32];                       // 32 columns at a time keeps the warp under 128 registers
+            tc::tmem_ld_32x32(taddr + half * 32, v);
+            tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[half][j]);
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          }
+          if (half == 1 && c + 2 >= nchunks) {     // this warp's share of the accumulator now lives in registers
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster_relaxed(tmem_empty_leader + ab * 8);
+          }
           if (ep.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -436,8 +634,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     tc::tmem_dealloc2(tmem_base, TMEM_COLS);
   }
   if (TRACE && threadIdx.x == 0) {
-    unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-    trace_put(ep, 0, clock64() - t_entry); trace_put(ep, 7, sm);
+    trace_put(ep, 0, clock64() - t_entry);
   }
 }
 
@@ -497,6 +694,9 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
     uint64_t dims[4] = {(uint64_t)sg.C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)sg.Bt};
     uint64_t str[3] = {(uint64_t)sg.C * 2, (uint64_t)p.W * sg.C * 2, (uint64_t)p.H * p.W * sg.C * 2};
     uint32_t box[4] = {(uint32_t)BK, (uint32_t)g.bw, (uint32_t)g.bh, (uint32_t)g.bn};
+    EO_REQUIRE(!sg.gn_scale || sg.patch, EO_ERR_ARG, "tc_conv3: GroupNorm can only be folded into a halo-patch segment");
+    EO_REQUIRE(!sg.gn_scale || (sg.gn_shift && sg.gn_ld % 4 == 0 && sg.gn_coff % 8 == 0), EO_ERR_ARG,
+               "tc_conv3: GroupNorm rows must be 16-byte aligned");
     if (sg.patch) {
       EO_REQUIRE(sg.ntaps == 9, EO_ERR_ARG, "tc_conv3: a patch segment has nine taps");
       for (int t = 0; t < 9; ++t)
@@ -510,13 +710,15 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
       // K order of a patch segment: (64-channel block, tap, channel)
       for (int c0 = 0; c0 < sg.C; c0 += BK) {
         KEnt3 e{}; e.seg = s; e.c0 = c0; e.patch = 1; e.kofs = kofs;
+        e.gn = sg.gn_scale ? (sg.silu ? 2 : 1) : 0; e.gnc = sg.gn_coff + c0;
         tab.push_back(e);
         kofs += 9 * BK;
       }
     } else {
       for (int t = 0; t < sg.ntaps; ++t)
         for (int c0 = 0; c0 < sg.C; c0 += BK) {
-          KEnt3 e{}; e.seg = s; e.c0 = c0; e.dh = sg.dh[t]; e.dw = sg.dw[t]; e.dn = sg.dn[t]; e.kofs = kofs;
+          KEnt3 e{}; e.seg = s; e.c0 = c0; e.dhw = ((int)sg.dh[t] & 0xffff) | ((int)sg.dw[t] << 16); e.dn = sg.dn[t]; e.kofs = kofs;
+          e.gn = sg.gn_scale ? (sg.silu ? 2 : 1) : 0; e.gnc = sg.gn_coff + c0;
           tab.push_back(e);
           kofs += BK;
         }
@@ -568,7 +770,11 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
   const int BN = pl->bn_tile;
   const bool has_res = p.residual != nullptr;
   const int b_bytes = (BN / 2) * 128;
-  const int fixed = Smem::VAR_OFF + (has_res ? 2 * STG_BYTES : 0);
+  // operand-A stages: all three to whoever fills them, two each when a conv has both kinds of load
+  bool any_gn = false, any_raw = false;
+  for (int s = 0; s < p.nseg; ++s) { if (p.seg[s].gn_scale) any_gn = true; else any_raw = true; }
+  const int SAR = any_raw ? (any_gn ? 2 : 3) : 0, SAG = any_gn ? (any_raw ? 2 : 3) : 0;
+  const int fixed = (SAR + SAG) * A_STAGE + Smem::VAR_OFF + (has_res ? 2 * STG_BYTES : 0);
   int SB = (SMEM_LIMIT - 1024 - fixed) / b_bytes;
   if (SB > MAX_SB) SB = MAX_SB;
   EO_REQUIRE(SB >= 2, EO_ERR_STATE, "tc_conv3: shared memory budget leaves %d weight stages", SB);
@@ -588,6 +794,15 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
   Epi3 ep{};
   ep.bias = p.bias; ep.bias_nc = p.bias_nc; ep.ld_bias_nc = p.ld_bias_nc; ep.stats = p.stats; ep.Cout = p.Cout;
   ep.has_res = has_res ? 1 : 0;
+  for (int s = 0; s < 3; ++s) {
+    const bool on = s < p.nseg && p.seg[s].gn_scale != nullptr;
+    ep.gn_scale[s] = on ? p.seg[s].gn_scale : nullptr;
+    ep.gn_shift[s] = on ? p.seg[s].gn_shift : nullptr;
+    ep.gn_ld[s] = on ? p.seg[s].gn_ld : 0;
+    ep.gn_src[s] = on ? p.seg[s].ptr : nullptr;
+    ep.gn_C[s] = on ? p.seg[s].C : 0;
+    ep.any_gn |= on ? 1 : 0;
+  }
   ep.trace = g_trace3; ep.trace_n = g_trace3_n;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * ncl));
@@ -600,7 +815,7 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
   cfg.attrs = attr; cfg.numAttrs = 1;
   auto kern = g_trace3 ? k_conv_tc3<true> : k_conv_tc3<false>;
   EO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA[0], pl->mapA[1], pl->mapA[2], pl->mapB, pl->mapOut,
-                                   pl->mapRes, (const KEnt3*)pl->d_kblks, pl->nkb, g, B, BN, SB, n_work, n_ntiles, ep));
+                                   pl->mapRes, (const KEnt3*)pl->d_kblks, pl->nkb, g, B, BN, SB, SAR, SAG, n_work, n_ntiles, ep));
   return EO_OK;
 }
 

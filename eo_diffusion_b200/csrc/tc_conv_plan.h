@@ -17,7 +17,10 @@ struct TileGeom {
 // ---- tc_conv3.cu
 // One operand-A load of the K loop: a plain 128-pixel tile shifted by (dh, dw) in image plane dn
 // (one weight tile follows), or a halo patch (nine weight tiles follow, one per tap).
-struct KEnt3 { int seg, c0, dh, dw, dn, kofs, patch, pad; };
+//   gn: 0 = operand loaded by TMA as is, 1 = GroupNorm affine folded in (x*scale + shift), 2 = affine + SiLU:
+//   the transform warps load the patch from global memory, apply it and write the operand stage;
+//   gnc = first channel of this load in the scale/shift rows
+struct KEnt3 { int seg, c0, dhw, dn, kofs, patch, gn, gnc; };   // dhw: dh in the low 16 bits, dw in the high
 struct Geom3 {
   int bw, bh, bn;
   int tiles_w, tiles_h;
@@ -29,6 +32,12 @@ struct Epi3 {
   int ld_bias_nc;
   double* stats;            // [B, Cout, 2] (sum, sum of squares) accumulated with atomics, or null
   int Cout, has_res;
+  const float* gn_scale[3];   // per segment: [B, gn_ld] rows of the GroupNorm it reads through, or null
+  const float* gn_shift[3];
+  int gn_ld[3];
+  const void* gn_src[3];      // the segment's bf16 NHWC activation (the transform warps load it themselves)
+  int gn_C[3];
+  int any_gn;
   long long* trace;         // development aid: [n][8] per-CTA counters, or null
   int trace_n;
 };

@@ -2,6 +2,7 @@
 same bf16-rounded operands, over shapes of the BASELINE UNet, plus a per-CTA counter summary of the
 persistent kernel (eo_debug_conv_trace).  usage: python tools/conv_check.py [trace]"""
 import math
+import os
 import sys
 
 import numpy as np
@@ -32,13 +33,15 @@ def case(B, H, W, Cin, Cout, k, res, seed=0, trace=False):
     if trace:
         L.eo_debug_conv_trace(None, 0)
     nb = max(1, min(B, 4))          # reference on a few images only (fp32 conv of 64 x 256^2 is slow)
-    want = F.conv2d(x[:nb].float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=k // 2)
+    gn_silu = os.environ.get("EO_TEST_GN", "") == "2" and k == 3 and H % 16 == 0 and W % 8 == 0 and Cin % 64 == 0
+    act = (lambda v: F.silu(v).to(torch.bfloat16).float()) if gn_silu else (lambda v: v)
+    want = F.conv2d(act(x[:nb].float()).permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=k // 2)
     if res:
         want = want + r[:nb].float().permute(0, 3, 1, 2)
     got = y[:nb].float().permute(0, 3, 1, 2)
     err = float((got - want).norm() / want.norm())
     last = y[B - 1].float().permute(2, 0, 1)
-    want_last = F.conv2d(x[B - 1:].float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=k // 2)[0]
+    want_last = F.conv2d(act(x[B - 1:].float()).permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=k // 2)[0]
     if res:
         want_last = want_last + r[B - 1].float().permute(2, 0, 1)
     err_last = float((last - want_last).norm() / want_last.norm())
@@ -53,7 +56,7 @@ def case(B, H, W, Cin, Cout, k, res, seed=0, trace=False):
             msg += (f"\n      CTA life {life:.0f} clk, tiles/CTA {np.median(lead[:, 6]):.0f}; MMA waits: operands "
                     f"{100 * np.median(lead[:, 1]) / life:.0f}% accumulator {100 * np.median(lead[:, 2]) / life:.0f}%; "
                     f"epilogue: waits {100 * np.median(t[:, 3]) / life:.0f}% busy {100 * np.median(t[:, 4]) / life:.0f}%; "
-                    f"producer waits {100 * np.median(t[:, 5]) / life:.0f}%; "
+                    f"producer waits {100 * np.median(t[:, 5]) / life:.0f}%; transform busy {100 * np.median(t[:, 7]) / life:.0f}%; "
                     f"{flops / life / 148 :.0f} flop/clk/SM")
     print(msg, flush=True)
     return max(err, err_last)
