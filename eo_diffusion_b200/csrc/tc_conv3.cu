@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
            const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
            const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
-           const KEnt3* __restrict__ ents, int nent, Geom3 g, int B, int BN, int SB, int SAR, int SAG, int n_work,
+           const KEnt3* __restrict__ ents, int nent, Geom3 g, int B, int BN, int SB, int TPB, int SAR, int SAG, int n_work,
            int n_ntiles, Epi3 ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_a = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);   // operand-A stages
@@ -158,7 +158,8 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_empty + 2);
   const bool has_res = ep.has_res != 0;
   uint8_t* res_sm = smem + Smem::VAR_OFF;
-  const int b_bytes = (BN / 2) * 128;
+  const int b_bytes = (BN / 2) * 128;          // one 64-deep weight tile (this CTA's half of the BN rows)
+  const int b_stage = TPB * b_bytes;           // a weight stage holds TPB tiles: the taps of one kernel row of a patch
   uint8_t* b_sm = res_sm + (has_res ? 2 * STG_BYTES : 0);
   uint8_t* stg_sm = smem + Smem::STG_OFF;
 
@@ -224,14 +225,18 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         }
         __syncwarp();
         if (!en.gn) ra.next((uint32_t)SAR);
+        // weight tiles of this load: 9 for a patch (TPB per stage), 1 otherwise
         const int nb = en.patch ? 9 : 1;
-        for (int j = 0; j < nb; ++j) {
+        const int per = en.patch ? TPB : 1;
+        for (int j = 0; j < nb; j += per) {
           { TRACE_T0(); tc::mbar_wait(&b_empty[rb.i], rb.ph ^ 1); TRACE_ACC(tr_wait); }
           if (tc::elect_one()) {
             // one arrival per phase: the leader's producer, which posts the byte count of BOTH CTAs'
             // loads; the peer's TMA only completes transactions on the leader's barrier
-            if (rank == 0) tc::mbar_arrive_expect_tx(&b_full[rb.i], 2 * b_bytes);
-            tc::tma2_load_2d(b_sm + rb.i * b_bytes, &mapB, b_full_l + rb.i * 8, en.kofs + j * BK, t.nbase + b_row);
+            if (rank == 0) tc::mbar_arrive_expect_tx(&b_full[rb.i], 2 * per * b_bytes);
+            for (int u = 0; u < per; ++u)
+              tc::tma2_load_2d(b_sm + rb.i * b_stage + u * b_bytes, &mapB, b_full_l + rb.i * 8, en.kofs + (j + u) * BK,
+                               t.nbase + b_row);
           }
           __syncwarp();
           rb.next((uint32_t)SB);
@@ -245,7 +250,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     if (rank == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(2 * BM, BN, 0, 0);
       const uint64_t bdesc0 = tc::make_sw128_desc(tc::smem_u32(b_sm));
-      const uint32_t b_step = (uint32_t)b_bytes >> 4;
+      const uint32_t b_step = (uint32_t)b_stage >> 4, b_tile = (uint32_t)b_bytes >> 4;
       Ring ra, rg, rb;
       uint32_t it = 0;
       long long tr_ops = 0, tr_acc = 0;
@@ -268,16 +273,22 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           const uint32_t a_base = tc::smem_u32(gn ? smem_g + rg.i * A_STAGE : smem_a + ra.i * A_STAGE);
           uint64_t* a_release = gn ? &g_empty[rg.i] : &r_empty[ra.i];
           const bool last_e = e == nent - 1;
-          // one weight tile: wait for it, issue the 4 K=16 MMAs of this 64-deep K block, release it
-          auto kblock = [&](uint64_t adesc, bool last_of_a) {
+          // one weight stage: wait for it, issue the 4 K=16 MMAs of each of its NT 64-deep K blocks (tile u
+          // against operand descriptor adesc + u * a_step), release it.  Issuing blocks the thread at the
+          // tensor pipe's pace and the wait / fence / commit around it are not hidden behind the pipe's
+          // short queue (measured: 415 clk per K block whatever the tile width below 256), so narrow
+          // tiles take a whole kernel row of taps per stage.
+          auto kgroup = [&](uint64_t adesc, uint32_t a_step, int nt, bool last_of_a) {
             { TRACE_T0(); tc::mbar_wait(&b_full[rb.i], rb.ph); TRACE_ACC(tr_ops); }
             tc::tc_fence_after();
             const uint64_t bdesc = bdesc0 + (uint64_t)(rb.i * b_step);
             if (tc::elect_one()) {
+              for (int u = 0; u < nt; ++u) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                tc::umma2_f16_ss(d_tmem, tc::desc_advance(adesc, k * 32), tc::desc_advance(bdesc, k * 32), idesc,
-                                 k ? 1u : acc);
+                for (int k = 0; k < BK / 16; ++k)
+                  tc::umma2_f16_ss(d_tmem, tc::desc_advance(adesc + (uint64_t)(u * a_step), k * 32),
+                                   tc::desc_advance(bdesc + (uint64_t)(u * b_tile), k * 32), idesc, (k | u) ? 1u : acc);
+              }
               tc::umma2_commit_mc(&b_empty[rb.i], 3);                   // frees the weight stage in both CTAs
               if (last_of_a) tc::umma2_commit_mc(a_release, 3);          // ... and the activation stage
               if (last_of_a && last_e) tc::umma2_commit_mc(&tmem_full[ab], 3);   // accumulator complete
@@ -289,11 +300,16 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           if (patch) {
             // tap (kh, kw) of a patch starts kh patch rows + kw pixels into it
             const uint64_t ad0 = tc::make_sw128_desc_sbo(a_base, PATCH_W * 128);
+            if (TPB == 3) {
 #pragma unroll
-            for (int j = 0; j < 9; ++j)
-              kblock(ad0 + (uint64_t)(((j / 3) * PATCH_W + (j % 3)) * 8), j == 8);
+              for (int kh = 0; kh < 3; ++kh) kgroup(ad0 + (uint64_t)(kh * PATCH_W * 8), 8u, 3, kh == 2);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 9; ++j)
+                kgroup(ad0 + (uint64_t)(((j / 3) * PATCH_W + (j % 3)) * 8), 0u, 1, j == 8);
+            }
           } else {
-            kblock(tc::make_sw128_desc(a_base), true);
+            kgroup(tc::make_sw128_desc(a_base), 0u, 1, true);
           }
           if (gn) rg.next((uint32_t)SAG); else ra.next((uint32_t)SAR);
         }
@@ -775,10 +791,15 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
   for (int s = 0; s < p.nseg; ++s) { if (p.seg[s].gn_scale) any_gn = true; else any_raw = true; }
   const int SAR = any_raw ? (any_gn ? 2 : 3) : 0, SAG = any_gn ? (any_raw ? 2 : 3) : 0;
   const int fixed = (SAR + SAG) * A_STAGE + Smem::VAR_OFF + (has_res ? 2 * STG_BYTES : 0);
-  int SB = (SMEM_LIMIT - 1024 - fixed) / b_bytes;
+  // narrow tiles: three weight tiles (one kernel row of a patch) per stage, see the MMA warp
+  bool any_patch = false;
+  for (int s = 0; s < p.nseg; ++s) any_patch |= p.seg[s].patch != 0;
+  const int TPB = (any_patch && BN <= 192) ? 3 : 1;
+  const int b_stage = TPB * b_bytes;
+  int SB = (SMEM_LIMIT - 1024 - fixed) / b_stage;
   if (SB > MAX_SB) SB = MAX_SB;
   EO_REQUIRE(SB >= 2, EO_ERR_STATE, "tc_conv3: shared memory budget leaves %d weight stages", SB);
-  const int dyn = fixed + SB * b_bytes + 1024;
+  const int dyn = fixed + SB * b_stage + 1024;
   if (!attr_set) {
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -815,7 +836,7 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
   cfg.attrs = attr; cfg.numAttrs = 1;
   auto kern = g_trace3 ? k_conv_tc3<true> : k_conv_tc3<false>;
   EO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA[0], pl->mapA[1], pl->mapA[2], pl->mapB, pl->mapOut,
-                                   pl->mapRes, (const KEnt3*)pl->d_kblks, pl->nkb, g, B, BN, SB, SAR, SAG, n_work, n_ntiles, ep));
+                                   pl->mapRes, (const KEnt3*)pl->d_kblks, pl->nkb, g, B, BN, SB, TPB, SAR, SAG, n_work, n_ntiles, ep));
   return EO_OK;
 }
 
