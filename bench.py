@@ -130,6 +130,22 @@ def measured_peaks():
         return dict(tflops=1590.0, gbs=6650.0, src="fallback")   # B200_PROFILING.md fallback (burst)
 
 
+def ncu_traffic(kernel, workload, batch):
+    """DRAM bytes (read + write) per launch of `kernel`, averaged over the launches of one UNet forward,
+    from the committed `ncu --set full` capture of this workload (profiles/*_traffic.json, written by
+    profiles/extract_traffic.py).  None when no capture matches."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                t = json.load(f)
+            if t.get("kernel") == kernel and t.get("workload") == workload and t.get("batch") == batch:
+                return t["dram_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
+
+
 # ----------------------------------------------------------------------------------------
 # CPU legs (the oracle port of the reference path): cpu_baseline and --impl reference
 # ----------------------------------------------------------------------------------------
@@ -305,12 +321,12 @@ def run_ours(args, wl):
             e["bytes"] += by.value * B
             e["launches"] += 1
         peaks = measured_peaks()
-        fam = "k_conv_tc" if "k_conv_tc" in breakdown else "k_conv_simt"
+        fam = next(k for k in ("k_conv_tc3", "k_conv_tc", "k_conv_simt") if k in breakdown)
         e = breakdown[fam]
         ach = e["flops"] / (e["ms"] * 1e-3) / 1e12
         total_ms = sum(v["ms"] for v in breakdown.values())
         roofline = {"bound": "tensor", "kernel": fam, "achieved": ach, "peak": peaks["tflops"],
-                    "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": ncu_traffic(fam, args.workload, B),
                     "peak_source": f"{peaks['src']} bf16_tflops_sustained",
                     "flops_per_launch_avg": e["flops"] / e["launches"], "launches_per_step": e["launches"],
                     "share_of_unet_time": e["ms"] / total_ms}

@@ -481,9 +481,12 @@ struct eo_unet {
     }
     return o;
   }
+  // write into a strided view of an existing activation instead of a new one (sub-pixel convs of Upsample)
+  struct OutView { Act target; long long off, sw, sh, sn; double alg_flops; };   // alg_flops: algorithmic FLOPs per image to report
   int plan_conv_tc(const std::string& name, const std::vector<TcSegSpec>& tsegs, const std::vector<PackSeg>& segs_in,
                    int Cout_rows, const int* d_row_map, const float* bias_a, const float* bias_b, int tb_off,
-                   const Act* residual, int Ho, int Wo, Act* out, cudaStream_t st, bool want_stats = true) {
+                   const Act* residual, int Ho, int Wo, Act* out, cudaStream_t st, bool want_stats = true,
+                   const OutView* view = nullptr) {
     std::vector<bool> patch;
     for (auto& ts : tsegs) patch.push_back(patchable(ts, Ho, Wo) && ts.act.C % 64 == 0);
     const std::vector<PackSeg> segs = patch_order(segs_in, patch);
@@ -493,11 +496,13 @@ struct eo_unet {
     float* bias = nullptr;
     if (bias_a || bias_b) { rc = pack_bias2(bias_a, bias_b, Cout_rows, d_row_map, &bias, st); if (rc) return rc; }
     last_packed_bias = bias;
-    Act o = new_act(Cout_rows, Ho, Wo);
-    if (want_stats && tc_conv_stats_supported(Ho, Wo)) {
+    Act o = view ? view->target : new_act(Cout_rows, Ho, Wo);
+    if (!view && want_stats && tc_conv_stats_supported(Ho, Wo)) {
       o.stats = (long long)ch_stats_floats;
       ch_stats_floats += (size_t)Bmax * Cout_rows * 2;
     }
+    const bool has_view = view != nullptr;
+    const OutView vw = view ? *view : OutView();
     Act res = residual ? *residual : Act();
     const bool has_res = residual != nullptr;
     std::vector<TcSegSpec> tv = tsegs;
@@ -521,11 +526,15 @@ struct eo_unet {
       if (tb_off >= 0) { p.bias_nc = tb + tb_off; p.ld_bias_nc = tb_total; }
       p.residual = has_res ? ptr(res.off) : nullptr;
       p.out = ptr(o.off);
+      if (has_view) {
+        p.out = ptr<__nv_bfloat16>(o.off) + vw.off;
+        p.out_sw = vw.sw; p.out_sh = vw.sh; p.out_sn = vw.sn;
+      }
       p.stats = o.stats >= 0 ? ch_stats + o.stats : nullptr;
       return tc_conv_plan_create(p, &tc_plans[plan_idx]);
     };
     push(name, [=](int B, cudaStream_t stx) -> int { return tc_conv_launch(tc_plans[plan_idx], B, stx); }, 1, prepare);
-    note("k_conv_tc", 2.0 * Ho * Wo * Cout_rows * K, 0);
+    note(tc_conv3_enabled() ? "k_conv_tc3" : "k_conv_tc", has_view ? vw.alg_flops : 2.0 * Ho * Wo * Cout_rows * K, 0);
     *out = o;
     return EO_OK;
   }
@@ -744,6 +753,36 @@ struct eo_unet {
     if (mode == EO_MODE_FP32) {
       SrcSpec s; s.act = x; s.ksize = 3;
       return plan_conv_fp32(L.prefix + "conv", {s}, {{wu, L.cin, 3, 0, L.cin}}, L.cout, w(p + "bias"), nullptr, -1, nullptr, 1, 1, out, st);
+    }
+    static int subpix = -1;
+    if (subpix < 0) { const char* e = std::getenv("EO_UP_SUBPIXEL"); subpix = (e && e[0] == '0') ? 0 : 1; }
+    if (subpix && tc_conv3_enabled() && tc_conv_stats_supported(x.H, x.W)) {
+      // Four sub-pixel convolutions over the low-resolution input, one per output parity (a, b), with the
+      // 3x3 taps that read the same source pixel summed (k_fold_upsample_weight): 4/9 of the FLOPs and no
+      // materialised upsampled tensor.  Each writes its quarter of the output through a strided view.
+      const int C = x.C, Ho = x.H * 2, Wo = x.W * 2;
+      Act o = new_act(L.cout, Ho, Wo);
+      o.stats = (long long)ch_stats_floats;
+      ch_stats_floats += (size_t)Bmax * L.cout * 2;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          float* wf = nullptr;
+          int rc = dmalloc(&wf, (size_t)L.cout * C * 4);
+          if (rc) return rc;
+          if ((rc = launch_fold_upsample_weight(wu, L.cout, C, a, b, wf, st))) return rc;
+          TcSegSpec sgm; sgm.act = x; sgm.ntaps = 4;
+          for (int t = 0; t < 4; ++t) { sgm.dh[t] = (int8_t)(a - 1 + t / 2); sgm.dw[t] = (int8_t)(b - 1 + t % 2); sgm.plane[t] = 0; }
+          // reported FLOPs stay the algorithmic ones of the 3x3 conv on the upsampled grid (a quarter per launch);
+          // the launch executes 4/9 of them
+          OutView vw{o, ((long long)a * Wo + b) * L.cout, 2LL * L.cout, 2LL * Wo * L.cout, (long long)Ho * Wo * L.cout,
+                     2.0 * x.H * x.W * L.cout * 9.0 * C};
+          Act dummy;
+          rc = plan_conv_tc(L.prefix + "conv.p" + std::to_string(a * 2 + b), {sgm}, {{wf, C, 2, 0, C}}, L.cout, nullptr,
+                            w(p + "bias"), nullptr, -1, nullptr, x.H, x.W, &dummy, st, true, &vw);
+          if (rc) return rc;
+        }
+      *out = o;
+      return EO_OK;
     }
     Act up = new_act(x.C, x.H * 2, x.W * 2);
     Act xx = x;

@@ -123,6 +123,9 @@ int launch_nhwc_to_nchw_f32(const void* src, int dt, float* dst, int B, int HW, 
 int launch_pack_conv_weight(const float* w, int Cin_total, int ksize, int cin_off, int C,
                             void* dst, int dst_dt, long long stride_n, long long stride_k,
                             int k_off, int Nout, const int* row_map, cudaStream_t st);
+// wf[Cout][Cin][2][2] = the 3x3 weights w[Cout][Cin][3][3] folded for output parity (a, b) of a nearest x2
+// upsample + conv3x3 (taps at low-resolution rows {a-1, a}, columns {b-1, b})
+int launch_fold_upsample_weight(const float* w, int Cout, int Cin, int a, int b, float* wf, cudaStream_t st);
 // dst[n] = (a ? a[row(n)] : 0) + (b ? b[row(n)] : 0)
 int launch_pack_bias(const float* a, const float* b, float* dst, int Nout, const int* row_map,
                      cudaStream_t st);
@@ -158,6 +161,9 @@ struct TcConvParams {
   int res_f32 = 0;
   void* out = nullptr;              // NHWC [B,H,W,Cout] (fp32 if out_f32, else bf16)
   int out_f32 = 0;
+  // persistent kernel only: `out` as a strided view (elements) -- pixel (n, h, w) at out + out_sn*n + out_sh*h +
+  // out_sw*w; 0 = dense NHWC.  Used by the sub-pixel convolutions of Upsample.
+  long long out_sw = 0, out_sh = 0, out_sn = 0;
   double* stats = nullptr;          // [B, Cout, 2] per-channel (sum, sum of squares) of `out`,
                                     // accumulated with atomics (zeroed by the caller), or null
 };

@@ -1005,6 +1005,36 @@ int launch_pack_conv_weight(const float* w, int Cin_total, int ksize, int cin_of
   return EO_OK;
 }
 
+namespace {
+// Nearest x2 upsampling followed by a 3x3 convolution (Upsample.forward, unet_openai.py:229-242) equals,
+// for output pixel (2h+a, 2w+b), a 2x2 convolution over the LOW-resolution input with taps at rows
+// {a-1, a} and columns {b-1, b}: the 3x3 taps that read the same source pixel are summed.
+//   a = 0: row -1 <- kh 0, row 0 <- kh 1+2;   a = 1: row 0 <- kh 0+1, row +1 <- kh 2   (same for columns)
+__global__ void k_fold_upsample_weight(const float* __restrict__ w, long long n_pairs, int a, int b,
+                                       float* __restrict__ wf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float* s = w + i * 9;
+    float rows[2][3];
+    for (int kw = 0; kw < 3; ++kw) {
+      rows[0][kw] = a == 0 ? s[kw] : s[kw] + s[3 + kw];
+      rows[1][kw] = a == 0 ? s[3 + kw] + s[6 + kw] : s[6 + kw];
+    }
+    for (int r = 0; r < 2; ++r) {
+      wf[i * 4 + r * 2 + 0] = b == 0 ? rows[r][0] : rows[r][0] + rows[r][1];
+      wf[i * 4 + r * 2 + 1] = b == 0 ? rows[r][1] + rows[r][2] : rows[r][2];
+    }
+  }
+}
+}  // namespace
+
+int launch_fold_upsample_weight(const float* w, int Cout, int Cin, int a, int b, float* wf, cudaStream_t st) {
+  const long long n = (long long)Cout * Cin;
+  k_fold_upsample_weight<<<ew_grid(n), 256, 0, st>>>(w, n, a, b, wf);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+
 int launch_pack_bias(const float* a, const float* b, float* dst, int Nout, const int* row_map,
                      cudaStream_t st) {
   k_pack_bias<<<(unsigned)ceil_div(Nout, 128), 128, 0, st>>>(a, b, dst, Nout, row_map);

@@ -35,6 +35,7 @@
 // Roofline: tensor pipe / MUFU.  Algorithmic FLOPs per launch = 4 * B * heads * T^2 * ch.
 #include "kernels.h"
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace eo {
 
@@ -104,7 +105,7 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 template <bool TRACE, bool LSUM_MMA>
 __global__ void __launch_bounds__(352, 1)
 k_attn_tc(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out, int T,
-          int heads, int ch, float scale_log2, long long* trace, int trace_n) {
+          int heads, int ch, float scale_log2, long long* trace, int trace_n, int stagger_ns) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -233,6 +234,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict
     const uint32_t p_base = tmem + lane_addr + TM_P + t * 64;
     float m = -INFINITY, l = 0.f;       // m: reference maximum (log2 domain) of everything accumulated so far
     long long tr_s = 0, tr_o = 0, tr_exp = 0, tr_redo = 0;
+    if (t == 1 && stagger_ns > 0) __nanosleep(stagger_ns);
 
     for (int hb = 0; hb < nhalf; ++hb) {
       const int buf = hb & 1;
@@ -396,10 +398,12 @@ int tc_attn_launch(const TcAttnPlan* pl, int B, cudaStream_t st) {
   // logits = (q . k) * ch^-1/2 ; softmax evaluated with exp2
   float scale_log2 = (1.0f / sqrtf((float)p.ch)) * 1.4426950408889634f;
   dim3 grid((unsigned)ceil_div(p.T, 2 * QT), (unsigned)p.heads, (unsigned)B);
+  static int stagger = -1;
+  if (stagger < 0) { const char* e = std::getenv("EO_ATTN_STAGGER"); stagger = e ? atoi(e) : 0; }
   auto kern = g_attn_trace ? (p.ones_col ? k_attn_tc<true, true> : k_attn_tc<true, false>)
                            : (p.ones_col ? k_attn_tc<false, true> : k_attn_tc<false, false>);
   kern<<<grid, 352, ATTN_SMEM, st>>>(pl->map, reinterpret_cast<__nv_bfloat16*>(p.out), p.T, p.heads, p.ch, scale_log2,
-                                     g_attn_trace, g_attn_trace_n);
+                                     g_attn_trace, g_attn_trace_n, stagger);
   EO_CHECK_LAUNCH();
   return EO_OK;
 }

@@ -245,7 +245,7 @@ int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out) {
     return EO_OK;
   }
   for (int s = 0; s < p.nseg; ++s)
-    if (p.seg[s].patch || p.seg[s].gn_scale) {
+    if (p.seg[s].patch || p.seg[s].gn_scale || p.out_sw) {
       delete pl;
       set_error("tc_conv: halo patches and folded GroupNorm need the persistent kernel");
       return EO_ERR_ARG;

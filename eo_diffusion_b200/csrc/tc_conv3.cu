@@ -755,6 +755,10 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
   {
     uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
     uint64_t str[3] = {(uint64_t)p.Cout * 2, (uint64_t)p.W * p.Cout * 2, (uint64_t)p.H * p.W * p.Cout * 2};
+    if (p.out_sw) {
+      EO_REQUIRE(!p.residual, EO_ERR_ARG, "tc_conv3: a strided output view takes no residual");
+      str[0] = (uint64_t)p.out_sw * 2; str[1] = (uint64_t)p.out_sh * 2; str[2] = (uint64_t)p.out_sn * 2;
+    }
     // output: one store per epilogue warp = the 32 pixels of its TMEM lane quadrant
     const uint32_t sw = (uint32_t)(g.bw < 32 ? g.bw : 32);
     const uint32_t sh = (uint32_t)(g.bh < (int)(32 / sw) ? g.bh : (int)(32 / sw));
