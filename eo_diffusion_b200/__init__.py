@@ -4,5 +4,6 @@ executed by the hand-written CUDA library libeo_b200.so (C ABI: include/eo_b200.
 from .unet import UNetModel  # noqa: F401
 from .diffusion import EODiffusion  # noqa: F401
 from .ddim import DDIMSampler  # noqa: F401
+from .checkpoint import load_checkpoint, make_checkpoint  # noqa: F401
 
-__all__ = ["UNetModel", "EODiffusion", "DDIMSampler"]
+__all__ = ["UNetModel", "EODiffusion", "DDIMSampler", "load_checkpoint", "make_checkpoint"]
