@@ -355,6 +355,302 @@ k_attn_tc(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict
   if (trc && threadIdx.x == 0) trc[0] = clock64() - t_entry;
 }
 
+
+// =====================================================================================================
+// k_attn_tc5: FOUR query tiles per CTA, 32-key quarter-blocks.
+//
+// The two-tile kernel above keeps the MUFU pipe 61 % busy (profiles/r01c_attn_tc_v4_ncu.txt: xu 61 %, tensor
+// 30 %; trace: 1740 clk per 64-key half-block of which the exp pass is 1150 and 400 are waits): with one warp of
+// each tile per scheduler, the fixed latencies of every hand-off (a satisfied mbarrier.try_wait alone costs
+// ~100 clk, tcgen05.ld, the maximum tree, the vote, tcgen05.st + wait) leave the other warp alone on the pipe.
+// Here each scheduler holds FOUR softmax warps (one per tile):
+//   * tensor memory per tile: two 32-column S buffers (fp32 logits of one 32-key quarter-block) + 64 columns
+//     O; P (packed bf16 pairs, 16 columns) is written over the first half of the S buffer it came from once
+//     the row has been read -- 4 x 128 = 512 columns;
+//   * S_q+1 was issued a whole exp pass before the softmax of quarter-block q ends (into the other buffer);
+//     S_q+2 is issued right behind P V_q, whose P it overwrites -- tcgen05.mma of one thread execute in order;
+//   * the reference maximum m is kept INTEGER (log2 domain), so raising it rescales O and l by an exact power
+//     of two.
+// Measured, clk per 64 keys and tile (tools/attn_trace.py, B200): two tiles 869; this kernel 701.  Variants
+// that lost: 64-key S aliased with P in ONE buffer per tile 731 (258 of them the serial P V -> S chain); three
+// tiles with Q in tensor memory (S as a TS MMA, 16 instead of 40 clk per step: an MMA with A in shared memory
+// costs (128 + N) * 32 B / 128 B/clk, tools/probe_mma_dep.cu) 763 -- the tensor pipe is not the limiter, the
+// fourth warp per scheduler is worth more; the same with separate P buffers and S released at tcgen05.ld 918,
+// and with the next row's tcgen05.ld software-pipelined into the exp pass 1090.
+// Warps (768 threads, registers redistributed with setmaxnreg): 0..3 MMA issuers of tile 0..3, 4 TMA loader
+// (5..7 idle), 8..23 softmax (tile (w-8)/4, TMEM lane quadrant w % 4).
+// =====================================================================================================
+constexpr int NT5 = 4;
+constexpr int KQ5 = 32;                      // keys per quarter-block
+constexpr int KV_STAGES5 = 4;
+constexpr int OFF5_Q = 0;
+constexpr int OFF5_K = OFF5_Q + NT5 * TILE_BYTES;
+constexpr int OFF5_V = OFF5_K + KV_STAGES5 * TILE_BYTES;
+constexpr int OFF5_BAR = OFF5_V + KV_STAGES5 * TILE_BYTES;
+// q_full, kv_full[S], kv_empty[S], s_full[4][2], p_full[4][2], pv_late[4], o_done[4]
+constexpr int N_BARS5 = 1 + 2 * KV_STAGES5 + 6 * NT5;
+constexpr int ATTN5_SMEM = OFF5_BAR + N_BARS5 * 8 + 16 + 1024;
+constexpr int ATTN5_THREADS = 768;
+constexpr int SM_WARP0 = 8;
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+
+// trace slots (TRACE instantiation): 0 lifetime; softmax warp of tile 0, quadrant 0: 1 waits on S, 2 tcgen05.ld
+// of the row, 3 maximum + vote (+ raise), 4 exponentials + packing, 5 tcgen05.st + hand-over; 6 issuer 0 waits
+// on P; 7 HALF-blocks (64 keys, comparable with k_attn_tc's slot)
+template <bool TRACE, bool LSUM_MMA>
+__global__ void __launch_bounds__(ATTN5_THREADS, 1)
+k_attn_tc5(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out, int T,
+           int heads, int ch, float scale_log2, long long* trace, int trace_n) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF5_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + KV_STAGES5;
+  uint64_t* s_full = kv_empty + KV_STAGES5;   // [tile][buffer]: S_q is complete
+  uint64_t* p_full = s_full + 2 * NT5;        // [tile][buffer], 128 arrivals: P_q is in tensor memory
+  uint64_t* pv_late = p_full + 2 * NT5;       // [tile]: the second-to-last P V has completed
+  uint64_t* o_done = pv_late + NT5;           // [tile]: the last P V has completed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + NT5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_entry = TRACE ? clock64() : 0;
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  long long* trc = (TRACE && cta_lin < trace_n) ? trace + (long long)cta_lin * 8 : nullptr;
+  const int q0 = blockIdx.x * NT5 * QT, h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = min(NT5, (T - q0 + QT - 1) / QT);
+  const int nblk = (T + KT - 1) / KT;
+  const int nq = (T + KQ5 - 1) / KQ5;          // quarter-blocks that hold at least one key
+  const int cq = h * 3 * HD, ck = cq + HD, cv = cq + 2 * HD;
+
+  if (warp == 4 && lane == 0) {
+    tc::tma_prefetch_desc(&map_qkv);
+    tc::mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES5; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], ntiles); }
+    for (int i = 0; i < 2 * NT5; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 128); }
+    for (int i = 0; i < NT5; ++i) { tc::mbar_init(&pv_late[i], 1); tc::mbar_init(&o_done[i], 1); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) { tc::tmem_alloc(tmem_ptr, TM_COLS); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  // 768 threads leave 80 registers each: the issue warpgroup drops to 40, the loader's to 24, the four softmax
+  // warpgroups grow to 104 (40 + 24 + 4 * 104 = 480 = 6 * 80)
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    // ---------------------------------------------------------------- MMA issuer of tile `warp`
+    if (warp < ntiles) {
+      const int t = warp;
+      constexpr uint32_t idesc_s = tc::make_idesc_bf16(128, KQ5, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = tc::make_idesc_bf16(128, HD, 0, 1);   // P (TMEM) x V (MN-major)
+      constexpr uint32_t TILE16 = TILE_BYTES >> 4, QUART16 = (KQ5 * 128) >> 4;
+      const uint64_t qdesc = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_Q)) + (uint64_t)(t * TILE16);
+      const uint64_t kdesc0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_K));
+      const uint64_t vdesc0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_V));
+      const uint32_t d_s = tmem + t * 128, d_o = d_s + 64;
+      const int ksteps = (ch + 15) >> 4;        // the padded channels of q and k are zero
+      // S_q = Q_t K_q^T into S buffer q & 1; quarter-block q = rows 32*(q & 3).. of the K tile in `stage`
+      auto issue_s = [&](int q, uint32_t stage) {
+        if (tc::elect_one()) {
+          const uint64_t kdesc = kdesc0 + (uint64_t)(stage * TILE16 + (q & 3) * QUART16);
+          const uint32_t d = d_s + (q & 1) * KQ5;
+          for (int k = 0; k < ksteps; ++k)
+            tc::umma_f16_ss(d, tc::desc_advance(qdesc, k * 32), tc::desc_advance(kdesc, k * 32), idesc_s, k != 0 ? 1u : 0u);
+          tc::umma_commit(&s_full[t * 2 + (q & 1)]);
+        }
+        __syncwarp();
+      };
+      // O_t (+)= P_q V_q; P_q = packed bf16 pairs in the first 16 columns of S buffer q & 1
+      auto issue_pv = [&](int q, uint32_t stage, bool release_kv, bool last) {
+        if (tc::elect_one()) {
+          const uint64_t vdesc = vdesc0 + (uint64_t)(stage * TILE16 + (q & 3) * QUART16);
+          const uint32_t pa = d_s + (q & 1) * KQ5;
+#pragma unroll
+          for (int k = 0; k < KQ5 / 16; ++k)     // A: 16 keys = 8 packed columns of P; B: 16 rows of 128 B of V
+            umma_f16_ts(d_o, pa + k * 8, tc::desc_advance(vdesc, k * 16 * 128), idesc_o, (q != 0 || k != 0) ? 1u : 0u);
+          if (q == nq - 2) tc::umma_commit(&pv_late[t]);      // only the last quarter-block's raise path needs it
+          if (release_kv) tc::umma_commit(&kv_empty[stage]);
+          if (last) tc::umma_commit(&o_done[t]);
+        }
+        __syncwarp();
+      };
+      long long tr_p = 0;
+      tc::mbar_wait(q_full, 0);
+      tc::mbar_wait(&kv_full[0], 0);
+      tc::tc_fence_after();
+      issue_s(0, 0);
+      if (nq > 1) issue_s(1, 0);
+      uint32_t st = 0;                  // stage of the K/V tile of quarter-block q
+      uint32_t st2 = 0, ph2 = 0;        // stage / phase of the K/V tile of quarter-block q + 2
+      for (int q = 0; q < nq; ++q) {
+        const bool last = q == nq - 1;
+        // the K/V tile of quarter-block q + 2 (a new one when q + 2 is a multiple of 4)
+        if (q + 2 < nq && ((q + 2) & 3) == 0) {
+          if (++st2 == KV_STAGES5) { st2 = 0; ph2 ^= 1; }
+          tc::mbar_wait(&kv_full[st2], ph2);
+        }
+        { ATR_T0(); tc::mbar_wait(&p_full[t * 2 + (q & 1)], (q >> 1) & 1); ATR_ACC(tr_p); }
+        tc::tc_fence_after();
+        issue_pv(q, st, (q & 3) == 3 || last, last);
+        if (q + 2 < nq) issue_s(q + 2, st2);      // in order behind P V_q, whose P it overwrites
+        if ((q & 3) == 3) { if (++st == KV_STAGES5) st = 0; }
+      }
+      if (trc && warp == 0 && lane == 0) { trc[6] = tr_p; trc[7] = (nq + 1) / 2; }
+    }
+  } else if (warp < SM_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    // ---------------------------------------------------------------- TMA loader (warp 4)
+    if (warp == 4) {
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(q_full, ntiles * TILE_BYTES);
+        for (int t = 0; t < ntiles; ++t)
+          tc::tma_load_3d(smem + OFF5_Q + t * TILE_BYTES, &map_qkv, q_full, cq, q0 + t * QT, b);
+      }
+      __syncwarp();
+      uint32_t s = 0, ph = 0;
+      for (int j = 0; j < nblk; ++j) {
+        tc::mbar_wait(&kv_empty[s], ph ^ 1);
+        if (tc::elect_one()) {
+          tc::mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+          tc::tma_load_3d(smem + OFF5_K + s * TILE_BYTES, &map_qkv, &kv_full[s], ck, j * KT, b);
+          tc::tma_load_3d(smem + OFF5_V + s * TILE_BYTES, &map_qkv, &kv_full[s], cv, j * KT, b);
+        }
+        __syncwarp();
+        if (++s == KV_STAGES5) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ---------------------------------------------------------------- softmax / output: thread <-> query row
+    const int t = (warp - SM_WARP0) >> 2;
+    if (t < ntiles) {
+      const int qd = warp & 3;
+      const int row = qd * 32 + lane;
+      const uint32_t sp = tmem + ((uint32_t)(qd * 32) << 16) + t * 128;   // the two S buffers (P over their first halves)
+      const uint32_t oa = sp + 64;
+      float m = -INFINITY, l = 0.f;          // m: integer-valued reference maximum (log2 domain)
+      long long tr_s = 0, tr_exp = 0, tr_ld = 0, tr_max = 0, tr_st = 0;
+
+      for (int q = 0; q < nq; ++q) {
+        const int buf = q & 1;
+        const uint32_t sb = sp + buf * KQ5;
+        { ATR_T0(); tc::mbar_wait(&s_full[t * 2 + buf], (q >> 1) & 1); ATR_ACC(tr_s); }
+        tc::tc_fence_after();
+        const int nvalid = T - q * KQ5;        // < KQ5 only in a ragged last quarter-block
+        uint32_t v[32], pk[16];
+        long long tq0 = TRACE ? clock64() : 0;
+        tc::tmem_ld_32x32(sb, v);
+        tc::tmem_ld_wait();
+        if (TRACE) { const long long c = clock64(); tr_ld += c - tq0; tq0 = c; }
+        if (nvalid < KQ5) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= nvalid) v[i] = 0xff800000u;   // -inf
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          mx[(i >> 1) & 3] = max3(mx[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        const float cm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2;
+        // warp-uniform decision (the TMEM accesses are warp-collective)
+        if (__any_sync(0xffffffffu, cm > m + RESCALE_THRESHOLD)) {
+          // raise the reference maximum: O and l scale by the exact power of two 2^(m_old - m_new)
+          const float m_new = fmaxf(m, ceilf(cm));
+          const float alpha = (m_new == m) ? 1.0f : ex2(m - m_new);     // first quarter-block: ex2(-inf) = 0
+          m = m_new;
+          l *= alpha;
+          if (q > 0) {
+            // P V_q-1 must have landed (s_full(q) only covers P V_q-2): S_q+1 was issued behind it, so its
+            // barrier says so too; the last quarter-block has a commit of its own
+            if (q + 1 < nq) tc::mbar_wait(&s_full[t * 2 + (buf ^ 1)], ((q + 1) >> 1) & 1);
+            else tc::mbar_wait(&pv_late[t], 0);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < HD; c += 16) {
+              uint32_t o[16];
+              tmem_ld_32x16(oa + c, o);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x16(oa + c, o);
+            }
+          }
+        }
+        if (TRACE) { const long long c = clock64(); tr_max += c - tq0; tq0 = c; }
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float p0 = ex2(fmaf(__uint_as_float(v[2 * k]), scale_log2, -m));
+          const float p1 = ex2(fmaf(__uint_as_float(v[2 * k + 1]), scale_log2, -m));
+          if (!LSUM_MMA) { rs0 += p0; rs1 += p1; }
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+          pk[k] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        if (TRACE) { const long long c = clock64(); tr_exp += c - tq0; tq0 = c; }
+        tmem_st_32x16(sb, pk);          // the row of S has been read: P goes over its first half
+        l += rs0 + rs1;
+        tmem_st_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(&p_full[t * 2 + buf]);
+        if (TRACE) { const long long c = clock64(); tr_st += c - tq0; }
+      }
+      if (trc && warp == SM_WARP0 && lane == 0) { trc[1] = tr_s; trc[2] = tr_ld; trc[3] = tr_max; trc[4] = tr_exp; trc[5] = tr_st; }
+      tc::mbar_wait(&o_done[t], 0);
+      tc::tc_fence_after();
+      const int qi = q0 + t * QT + row;
+      __nv_bfloat16* op = out + ((long long)b * T + qi) * (heads * ch) + h * ch;
+      float inv = 1.0f / l;
+#pragma unroll
+      for (int c = HD - 32; c >= 0; c -= 32) {      // upper half first: it holds the row sum
+        uint32_t o[32];
+        tc::tmem_ld_32x32(oa + c, o);
+        tc::tmem_ld_wait();
+        if (LSUM_MMA && c == HD - 32) inv = 1.0f / __uint_as_float(o[31]);
+        if (qi < T) {
+#pragma unroll
+          for (int d = 0; d < 32; d += 8) {
+            if (c + d < ch) {
+              uint4 w4;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                h2[e] = __floats2bfloat162_rn(__uint_as_float(o[d + 2 * e]) * inv,
+                                              __uint_as_float(o[d + 2 * e + 1]) * inv);
+              *reinterpret_cast<uint4*>(op + c + d) = w4;
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, TM_COLS);
+  }
+  if (trc && threadIdx.x == 0) trc[0] = clock64() - t_entry;
+}
+
 long long* g_attn_trace = nullptr;
 int g_attn_trace_n = 0;
 
@@ -387,23 +683,37 @@ void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
 
 int tc_attn_launch(const TcAttnPlan* pl, int B, cudaStream_t st) {
   static bool attr_set = false;
+  static int stagger = 0, use_v4 = 0;
   if (!attr_set) {
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
+    const char* e = std::getenv("EO_ATTN_STAGGER");
+    stagger = e ? atoi(e) : 0;
+    e = std::getenv("EO_ATTN_V4");            // A/B switch: the two-tile kernel
+    use_v4 = e ? atoi(e) : 0;
     attr_set = true;
   }
   const TcAttnParams& p = pl->p;
   // logits = (q . k) * ch^-1/2 ; softmax evaluated with exp2
   float scale_log2 = (1.0f / sqrtf((float)p.ch)) * 1.4426950408889634f;
-  dim3 grid((unsigned)ceil_div(p.T, 2 * QT), (unsigned)p.heads, (unsigned)B);
-  static int stagger = -1;
-  if (stagger < 0) { const char* e = std::getenv("EO_ATTN_STAGGER"); stagger = e ? atoi(e) : 0; }
-  auto kern = g_attn_trace ? (p.ones_col ? k_attn_tc<true, true> : k_attn_tc<true, false>)
-                           : (p.ones_col ? k_attn_tc<false, true> : k_attn_tc<false, false>);
-  kern<<<grid, 352, ATTN_SMEM, st>>>(pl->map, reinterpret_cast<__nv_bfloat16*>(p.out), p.T, p.heads, p.ch, scale_log2,
-                                     g_attn_trace, g_attn_trace_n, stagger);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  if (use_v4) {
+    dim3 grid((unsigned)ceil_div(p.T, 2 * QT), (unsigned)p.heads, (unsigned)B);
+    auto kern = g_attn_trace ? (p.ones_col ? k_attn_tc<true, true> : k_attn_tc<true, false>)
+                             : (p.ones_col ? k_attn_tc<false, true> : k_attn_tc<false, false>);
+    kern<<<grid, 352, ATTN_SMEM, st>>>(pl->map, out, p.T, p.heads, p.ch, scale_log2, g_attn_trace, g_attn_trace_n, stagger);
+  } else {
+    dim3 grid((unsigned)ceil_div(p.T, NT5 * QT), (unsigned)p.heads, (unsigned)B);
+    auto kern = g_attn_trace ? (p.ones_col ? k_attn_tc5<true, true> : k_attn_tc5<true, false>)
+                             : (p.ones_col ? k_attn_tc5<false, true> : k_attn_tc5<false, false>);
+    kern<<<grid, ATTN5_THREADS, ATTN5_SMEM, st>>>(pl->map, out, p.T, p.heads, p.ch, scale_log2, g_attn_trace, g_attn_trace_n);
+  }
   EO_CHECK_LAUNCH();
   return EO_OK;
 }

@@ -57,10 +57,13 @@ def _attn_ref(qkv, heads, ch):
 
 @pytest.mark.parametrize("B,T,heads,ch", [
     (1, 128, 1, 64), (2, 256, 4, 32), (1, 64, 8, 64), (2, 1024, 8, 48), (1, 4096, 2, 48), (1, 320, 2, 16),
+    # ragged sequence lengths: a last half-block of < 32 and < 64 keys, a CTA with one, two and three query tiles
+    (1, 100, 2, 48), (2, 576, 2, 64), (1, 40, 1, 64), (1, 1000, 1, 48), (1, 1336, 1, 64),
 ])
-def test_attention_tc(cuda_dev, B, T, heads, ch):
+@pytest.mark.parametrize("gain", [1.5, 6.0])      # 6.0: logits of +-100, the reference maximum keeps moving
+def test_attention_tc(cuda_dev, B, T, heads, ch, gain):
     g = torch.Generator().manual_seed(T + heads + ch)
-    qkv = (torch.randn((B, T, heads * 3 * ch), generator=g) * 1.5).to(cuda_dev).to(torch.bfloat16)
+    qkv = (torch.randn((B, T, heads * 3 * ch), generator=g) * gain).to(cuda_dev).to(torch.bfloat16)
     out = torch.empty((B, T, heads * ch), dtype=torch.bfloat16, device=cuda_dev)
     _lib.check(_lib.lib().eo_test_attention_tc(_lib.ptr(qkv), _lib.ptr(out), B, T, heads, ch,
                                                _lib.stream_ptr()), "eo_test_attention_tc")

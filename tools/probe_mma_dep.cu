@@ -135,6 +135,7 @@ int main() {
   long long* d;
   cudaMalloc(&d, 64);
   const int iters = 512;
+  run<32, 1>(d, iters); run<32, 2>(d, iters); run<32, 4>(d, iters);
   run<64, 1>(d, iters); run<64, 2>(d, iters); run<64, 4>(d, iters);
   run<128, 1>(d, iters); run<128, 2>(d, iters); run<128, 4>(d, iters);
   run<256, 1>(d, iters); run<256, 2>(d, iters);
@@ -142,6 +143,6 @@ int main() {
   for (int sh : {11}) { run<64, 1>(d, iters, sh, 1280); run<128, 1>(d, iters, sh, 1280); run<256, 1>(d, iters, sh, 1280); }
   run<64, 1>(d, iters, 1, 1024); run<64, 1>(d, iters, 0, 2048);
   for (int it : {1, 2, 4, 8, 16, 64}) run<128, 1>(d, it);
-  run_ts<64, 0>(d, iters); run_ts<64, 1>(d, iters); run_ts<128, 0>(d, iters); run_ts<128, 1>(d, iters); run_ts<256, 1>(d, iters);
+  run_ts<32, 1>(d, iters); run_ts<64, 0>(d, iters); run_ts<64, 1>(d, iters); run_ts<128, 0>(d, iters); run_ts<128, 1>(d, iters); run_ts<256, 1>(d, iters);
   return 0;
 }
