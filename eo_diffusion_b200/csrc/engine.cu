@@ -486,7 +486,7 @@ struct eo_unet {
   int plan_conv_tc(const std::string& name, const std::vector<TcSegSpec>& tsegs, const std::vector<PackSeg>& segs_in,
                    int Cout_rows, const int* d_row_map, const float* bias_a, const float* bias_b, int tb_off,
                    const Act* residual, int Ho, int Wo, Act* out, cudaStream_t st, bool want_stats = true,
-                   const OutView* view = nullptr) {
+                   const OutView* view = nullptr, double alg_flops = -1.0) {
     std::vector<bool> patch;
     for (auto& ts : tsegs) patch.push_back(patchable(ts, Ho, Wo) && ts.act.C % 64 == 0);
     const std::vector<PackSeg> segs = patch_order(segs_in, patch);
@@ -534,7 +534,8 @@ struct eo_unet {
       return tc_conv_plan_create(p, &tc_plans[plan_idx]);
     };
     push(name, [=](int B, cudaStream_t stx) -> int { return tc_conv_launch(tc_plans[plan_idx], B, stx); }, 1, prepare);
-    note(tc_conv3_enabled() ? "k_conv_tc3" : "k_conv_tc", has_view ? vw.alg_flops : 2.0 * Ho * Wo * Cout_rows * K, 0);
+    note(tc_conv3_enabled() ? "k_conv_tc3" : "k_conv_tc",
+         has_view ? vw.alg_flops : alg_flops >= 0 ? alg_flops : 2.0 * Ho * Wo * Cout_rows * K, 0);
     *out = o;
     return EO_OK;
   }
@@ -910,6 +911,28 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
 
   // ---- stem: conv3x3 over cat(x, cond), NCHW fp32 -> NHWC (unet_openai.py:754-756, :608)
   Act h;
+  static int tc_ends = -1;      // EO_TC_ENDS=0: the SIMT stem and head (A/B switch)
+  if (tc_ends < 0) { const char* e = std::getenv("EO_TC_ENDS"); tc_ends = (e && e[0] == '0') ? 0 : 1; }
+  const Layer& L0 = in_blocks[0].layers[0];
+  if (mode == EO_MODE_BF16 && tc_ends && tc_conv3_enabled() && 18 * L0.cin <= 64 && L0.cout % 64 == 0) {
+    // few input channels: the 3x3 windows (bf16 value + rounding residual of every element, exact to 2^-17)
+    // become one 64-channel pixel, and the stem a 64-deep 1x1 convolution on the tensor cores, GroupNorm
+    // statistics of its output included
+    Act col = new_act(64, H, W);
+    const int cin = L0.cin;
+    push("input_blocks.0.im2col", [=](int B, cudaStream_t s) -> int {
+      if (io_cx + io_cc != cin) { set_error("stem: %d + %d input channels, expected %d", io_cx, io_cc, cin); return EO_ERR_ARG; }
+      return launch_stem_im2col(io_x, io_cx, io_cond, io_cc, ptr(col.off), B, H, W, s);
+    });
+    note("k_stem_im2col", 0, (double)H * W * (64 * 2 + cin * 4));
+    float* w2 = nullptr;
+    if ((rc = dmalloc(&w2, (size_t)L0.cout * 64))) return rc;
+    if ((rc = launch_stem_weight(w(L0.prefix + "weight"), L0.cout, cin, w2, st))) return rc;
+    if ((rc = plan_conv_tc("input_blocks.0", {seg1x1(col)}, {{w2, 64, 1, 0, 64}}, L0.cout, nullptr, w(L0.prefix + "bias"), nullptr,
+                           -1, nullptr, H, W, &h, st, true, nullptr, 2.0 * H * W * L0.cout * 9 * cin)))
+      return rc;
+    free_act(col);
+  } else
   {
     const Layer& L = in_blocks[0].layers[0];
     float* Wp = nullptr; int K = 0;
@@ -978,7 +1001,25 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
     h = o; named[out_blocks[i].name] = h;
   }
   // ---- head: conv3x3(SiLU(GN(h))) -> NCHW fp32 (unet_openai.py:739-743, :780)
-  {
+  if (mode == EO_MODE_BF16 && tc_ends && cfg.out_channels <= 64 && can_fuse_gn(3, H, W, final_ch)) {
+    // on the tensor cores with the output channels padded to one 64-wide tile (zero weight rows) and
+    // GroupNorm + SiLU folded into the operand load; a layout pass extracts the real channels
+    GnOut g = plan_gn("out.0", h, nullptr, w("out.0.weight"), w("out.0.bias"));
+    const int cout = cfg.out_channels, C = final_ch;
+    std::vector<int> rmap(64, -1);
+    for (int n = 0; n < cout; ++n) rmap[n] = n;
+    int* d_rmap = nullptr;
+    if ((rc = dmalloc(&d_rmap, (size_t)64))) return rc;
+    EO_CHECK_CUDA(cudaMemcpyAsync(d_rmap, rmap.data(), 64 * sizeof(int), cudaMemcpyHostToDevice, st));
+    EO_CHECK_CUDA(cudaStreamSynchronize(st));   // rmap is a stack-lifetime host buffer
+    Act o64;
+    if ((rc = plan_conv_tc("out", {with_gn(seg3x3(h), g, 0, 1)}, {{w("out.2.weight"), C, 3, 0, C}}, 64, d_rmap, w("out.2.bias"),
+                           nullptr, -1, nullptr, H, W, &o64, st, false, nullptr, 2.0 * H * W * cout * 9 * C)))
+      return rc;
+    free_gn(g);
+    push("out.nchw", [=](int B, cudaStream_t s) -> int { return launch_head_to_nchw(ptr(o64.off), 64, io_out, B, H * W, cout, s); });
+    note("k_head_to_nchw", 0, (double)H * W * (32 + cout * 4));
+  } else {
     GnOut g = plan_gn("out.0", h, nullptr, w("out.0.weight"), w("out.0.bias"));
     float* Wp = nullptr; int K = 0;
     if ((rc = pack_simt({{w("out.2.weight"), final_ch, 3, 0, final_ch}}, cfg.out_channels, &Wp, &K, st))) return rc;

@@ -108,6 +108,12 @@ int launch_upsample2x(const void* src, void* dst, int B, int H, int W, int C, cu
 // dst[(hp*2+wp)][b][h2][w2][c] = src[b][2*h2+hp][2*w2+wp][c]; planes are Bstride images apart
 int launch_space_to_depth(const void* src, void* dst, int B, int Bstride, int H, int W, int C,
                           cudaStream_t st);
+// tensor-core stem (<= 3 input channels): im2col of cat(x, cond) (NCHW fp32) into 64-channel bf16 NHWC pixels,
+// channels (tap, c) rounded to bf16 then their rounding residuals; and the matching [Cout][64] fp32 weights
+int launch_stem_im2col(const float* x, int Cx, const float* cond, int Cc, void* dst, int B, int H, int W, cudaStream_t st);
+int launch_stem_weight(const float* w, int Cout, int C, float* w2, cudaStream_t st);
+// tensor-core head: the first C of `ld` channels of a bf16 NHWC tensor -> NCHW fp32
+int launch_head_to_nchw(const void* src_bf16, int ld, float* dst, int B, int HW, int C, cudaStream_t st);
 // generic NHWC (dt) -> NCHW fp32 copy, for eo_unet_read_activation
 int launch_nhwc_to_nchw_f32(const void* src, int dt, float* dst, int B, int HW, int C,
                             cudaStream_t st);

@@ -961,6 +961,103 @@ int launch_nhwc_to_nchw_f32(const void* src, int dt, float* dst, int B, int HW, 
 }
 
 // =======================================================================================
+// tensor-core stem and head (bf16 mode): layout passes either side of k_conv_tc
+// =======================================================================================
+namespace {
+// im2col of the few-channel network input for the stem conv (unet_openai.py:608, :754-756): one 64-channel
+// bf16 NHWC pixel per output pixel, channels [0, 9C) = the 3x3 window of cat(x, cond) ordered (tap, channel)
+// rounded to bf16, channels [9C, 18C) = the rounding residuals (x - bf16(x), exact to 2^-17), rest zero.  The
+// stem is then a 64-deep 1x1 convolution on the tensor cores with the weights repeated for both halves.
+template <int C>
+__global__ void __launch_bounds__(256)
+k_stem_im2col(const float* __restrict__ x, int Cx, const float* __restrict__ cond, int Cc, __nv_bfloat16* __restrict__ dst,
+              int H, int W, long long npix) {
+  // one thread per pixel: 9 C coalesced loads (neighbouring threads read neighbouring pixels of an NCHW row),
+  // 64 bf16 built in registers, eight 16-byte stores
+  const long long HW = (long long)H * W;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(pix / HW);
+    const int r = (int)(pix - (long long)b * HW);
+    const int oh = r / W, ow = r - oh * W;
+    float v[9 * C];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ih = oh + tap / 3 - 1, iw = ow + tap % 3 - 1;
+      const bool in = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float* src = c < Cx ? x + ((long long)b * Cx + c) * HW : cond + ((long long)b * Cc + (c - Cx)) * HW;
+        v[tap * C + c] = in ? __ldg(src + (long long)ih * W + iw) : 0.f;
+      }
+    }
+    __align__(16) __nv_bfloat16 e[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+      float f = 0.f;
+      if (k < 9 * C) f = v[k];
+      else if (k < 18 * C) f = v[k - 9 * C] - __bfloat162float(__float2bfloat16_rn(v[k - 9 * C]));
+      e[k] = __float2bfloat16_rn(f);
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + pix * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = reinterpret_cast<const uint4*>(e)[j];
+  }
+}
+// w [Cout][C][3][3] -> w2 [Cout][64] matching k_stem_im2col's channel order
+__global__ void k_stem_weight(const float* __restrict__ w, int Cout, int C, float* __restrict__ w2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 64) return;
+  const int n = i >> 6;
+  int k = i & 63;
+  if (k >= 9 * C) k -= 9 * C;
+  float v = 0.f;
+  if (k < 9 * C) { const int tap = k / C, c = k - tap * C; v = w[((long long)n * C + c) * 9 + tap]; }
+  w2[i] = v;
+}
+// dst[b, c, p] (NCHW fp32, c < C) = src[b, p, c] (NHWC bf16 with `ld` channels per pixel)
+__global__ void __launch_bounds__(256)
+k_head_to_nchw(const __nv_bfloat16* __restrict__ src, int ld, float* __restrict__ dst, int HW, int C, long long npix) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW;
+    const int p = (int)(i - b * HW);
+    const __nv_bfloat16* s = src + i * ld;
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(s + c0));
+      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < C) dst[(b * C + c0 + j) * HW + p] = __bfloat162float(e[j]);
+    }
+  }
+}
+}  // namespace
+
+int launch_stem_im2col(const float* x, int Cx, const float* cond, int Cc, void* dst, int B, int H, int W, cudaStream_t st) {
+  EO_REQUIRE(18 * (Cx + Cc) <= 64, EO_ERR_ARG, "stem_im2col: %d input channels do not fit one 64-deep K block", Cx + Cc);
+  const long long npix = (long long)B * H * W;
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+  switch (Cx + Cc) {
+    case 1: k_stem_im2col<1><<<ew_grid(npix), 256, 0, st>>>(x, Cx, cond, Cc, d, H, W, npix); break;
+    case 2: k_stem_im2col<2><<<ew_grid(npix), 256, 0, st>>>(x, Cx, cond, Cc, d, H, W, npix); break;
+    default: k_stem_im2col<3><<<ew_grid(npix), 256, 0, st>>>(x, Cx, cond, Cc, d, H, W, npix); break;
+  }
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+int launch_stem_weight(const float* w, int Cout, int C, float* w2, cudaStream_t st) {
+  k_stem_weight<<<ceil_div(Cout * 64, 256), 256, 0, st>>>(w, Cout, C, w2);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+int launch_head_to_nchw(const void* src_bf16, int ld, float* dst, int B, int HW, int C, cudaStream_t st) {
+  EO_REQUIRE(ld % 8 == 0, EO_ERR_ARG, "head_to_nchw: ld %% 8");
+  const long long npix = (long long)B * HW;
+  k_head_to_nchw<<<ew_grid(npix), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src_bf16), ld, dst, HW, C, npix);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+
+// =======================================================================================
 // weight packing
 // =======================================================================================
 namespace {

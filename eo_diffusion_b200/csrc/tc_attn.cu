@@ -67,6 +67,19 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// 2^x on the FMA pipe (k_attn_tc5 takes every fourth pair of exponentials off the MUFU pipe, its limiter):
+// x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (relative error 7.5e-5,
+// 26 times below the bf16 rounding of P), 2^n added into the exponent field.  x <= 127 - 1; below -125 clamps.
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                   // 1.5 * 2^23: the integer lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.0551716685295105f, f, 0.2426111251115799f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t v[32]) {
@@ -392,6 +405,10 @@ constexpr int N_BARS5 = 1 + 2 * KV_STAGES5 + 6 * NT5;
 constexpr int ATTN5_SMEM = OFF5_BAR + N_BARS5 * 8 + 16 + 1024;
 constexpr int ATTN5_THREADS = 768;
 constexpr int SM_WARP0 = 8;
+#ifndef EO_ATTN_POLY_EVERY
+#define EO_ATTN_POLY_EVERY 4
+#endif
+constexpr int POLY_EVERY = EO_ATTN_POLY_EVERY;   // every n-th pair of exponentials runs on the FMA pipe (0 = none)
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t v[16]) {
   asm volatile(
@@ -598,8 +615,11 @@ k_attn_tc5(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float p0 = ex2(fmaf(__uint_as_float(v[2 * k]), scale_log2, -m));
-          const float p1 = ex2(fmaf(__uint_as_float(v[2 * k + 1]), scale_log2, -m));
+          const float x0 = fmaf(__uint_as_float(v[2 * k]), scale_log2, -m);
+          const float x1 = fmaf(__uint_as_float(v[2 * k + 1]), scale_log2, -m);
+          const bool on_fma = POLY_EVERY > 0 && (k % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == (POLY_EVERY - 1);
+          const float p0 = on_fma ? ex2_fma(x0) : ex2(x0);
+          const float p1 = on_fma ? ex2_fma(x1) : ex2(x1);
           if (!LSUM_MMA) { rs0 += p0; rs1 += p1; }
           __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
           pk[k] = *reinterpret_cast<uint32_t*>(&h2);
