@@ -63,6 +63,11 @@ SIGNATURES = {
     "eo_ddpm_step_mix": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "eo_ddim_step": (_I, [_P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _L, _P]),
     "eo_cfg_combine": (_I, [_P, _P, _F, _P, _L, _P]),
+    "eo_post_map": (_I, [_P, _P, _L, _I, _F, _P]),
+    "eo_post_dim_masked": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "eo_post_stats": (_I, [_P, _L, _P, _P, _P]),
+    "eo_psnr": (_I, [_P, _P, _L, _F, _P, _P, _P]),
+    "eo_ssim": (_I, [_P, _P, _I, _I, _I, _I, _F, C.POINTER(_F), _P, _P, _P, _P]),
     "eo_test_conv_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "eo_test_attention_tc": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "eo_debug_conv_trace": (_I, [_P, _I]),

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeo_b200.so")
-SOURCES = ["engine.cu", "simt.cu", "sampler.cu", "tc_conv.cu", "tc_conv3.cu", "tc_attn.cu"]
+SOURCES = ["engine.cu", "simt.cu", "sampler.cu", "tc_conv.cu", "tc_conv3.cu", "tc_attn.cu", "post.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -197,6 +197,30 @@ EO_API int eo_cfg_combine(const float* e_uncond, const float* e_cond, float scal
                    int64_t n_elems, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Post-processing of finished samples and image-quality metrics (reference inference.py:128-150;
+ * SURVEY.md 8f row 2).  Elementwise passes are bit-exact with the reference's fp32 torch ops.
+ * ---------------------------------------------------------------------------------- */
+/* out = clip(x, 0, 1) (mode 0, inference.py:128), (x + 1) / 2 (mode 1, :128/:136), or torchvision
+ * adjust_brightness(x, factor) = clip(factor * x, 0, 1) for float images (mode 2, :141-142, :149).
+ * out may alias x. */
+EO_API int eo_post_map(const float* x, float* out, int64_t n, int mode, float factor, void* stream);
+/* out[b,c,p] = image[b,c,p] * clip(mask[b,0,p] + 0.7, 0, 1)   (inference.py:135) */
+EO_API int eo_post_dim_masked(const float* image, const float* mask, float* out, int B, int C, int HW, void* stream);
+/* out3 = {mean, min, max} of x (the values the reference's host branches read: image.min() :128,
+ * gt.mean() / cond.mean() / samples.mean() :141-149).  workspace4: 4 doubles of device scratch. */
+EO_API int eo_post_stats(const float* x, int64_t n, double* workspace4, float* out3, void* stream);
+/* torchmetrics peak_signal_noise_ratio(preds, target, data_range) with the default reduction over the
+ * whole batch: out1[0] = 10 log10(data_range^2 / mean((preds - target)^2))   (inference.py:138) */
+EO_API int eo_psnr(const float* preds, const float* target, int64_t n, float data_range, double* workspace4,
+            float* out1, void* stream);
+/* torchmetrics structural_similarity_index_measure(preds, target, data_range) with its defaults (Gaussian
+ * 11 x 11 window, sigma 1.5, k1 0.01, k2 0.03, mean over the batch).  preds, target [B,C,H,W];
+ * gauss11: HOST array of the 11 normalised fp32 window weights (the host computes them with torchmetrics'
+ * op sequence); workspaceB: B doubles of device scratch; per_image_or_null [B], mean_out [1] on device. */
+EO_API int eo_ssim(const float* preds, const float* target, int B, int C, int H, int W, float data_range,
+            const float* gauss11, double* workspaceB, float* per_image_or_null, float* mean_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Kernel self-tests (used by tests/ on the GPU box): run one tensor-core implicit-GEMM
  * convolution / one attention call on caller-provided buffers, outside any UNet.
  * ---------------------------------------------------------------------------------- */
