@@ -143,10 +143,28 @@ struct eo_unet {
   const float* io_cond = nullptr; int io_cc = 0;
   const int64_t* io_t = nullptr; const int64_t* io_y = nullptr;
   float* io_out = nullptr;
+  // CUDA-graph replay of the forward for launch-bound sizes (EO_GRAPH=0 never, 1 always, default: when
+  // B*H*W <= 65536).  The graph reads its inputs from / writes its output to engine-owned staging buffers,
+  // so one instantiation serves every step of a sampling loop; key = (B, Cx, Cc, has y).
+  struct GraphSlot { int seen = 0; bool failed = false; cudaGraphExec_t exec = nullptr; };
+  std::map<long long, GraphSlot> graphs;
+  cudaStream_t graph_stream = nullptr;          // capture stream (the caller's may be the legacy default stream)
+  float *gs_x = nullptr, *gs_cond = nullptr, *gs_out = nullptr;
+  int64_t *gs_t = nullptr, *gs_y = nullptr;
+  void release_graphs() {
+    for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs.clear();
+    if (graph_stream) { cudaStreamDestroy(graph_stream); graph_stream = nullptr; }
+    gs_x = gs_cond = gs_out = nullptr; gs_t = gs_y = nullptr;   // freed with `owned`
+  }
+  int run_ops(int B, cudaStream_t st);
+  int forward_graph(const float* x, int Cx, const float* cond, int Cc, const int64_t* t, const int64_t* y, float* out,
+                    int B, cudaStream_t st, bool* handled);
 
   ~eo_unet() { release_plan(); }
 
   void release_plan() {
+    release_graphs();
     for (auto* p : tc_plans) tc_conv_plan_destroy(p);
     for (auto* p : attn_plans) tc_attn_plan_destroy(p);
     tc_plans.clear(); attn_plans.clear();
@@ -1076,34 +1094,100 @@ int eo_unet::forward(const float* x, int Cx, const float* cond, int Cc, const in
   // reference assert, unet_openai.py:758-760
   EO_REQUIRE((y != nullptr) == (cfg.num_classes > 0), EO_ERR_ARG,
              "must specify y if and only if the model is class-conditional");
+  if (!ms_per_op) {
+    bool handled = false;
+    int rc = forward_graph(x, Cx, cond, Cc, t, y, out, B, st, &handled);
+    if (rc || handled) return rc;
+  }
   io_x = x; io_cx = Cx; io_cond = cond; io_cc = Cc; io_t = t; io_y = y; io_out = out;
+  if (!ms_per_op) return run_ops(B, st);
   EO_CHECK_CUDA(cudaMemsetAsync(gn_sums, 0, (size_t)std::max(n_gn, 1) * Bmax * 64 * sizeof(double), st));
   if (ch_stats_floats) EO_CHECK_CUDA(cudaMemsetAsync(ch_stats, 0, ch_stats_floats * sizeof(double), st));
-  std::vector<cudaEvent_t> ev;
-  if (ms_per_op) {   // profiling variant: one CUDA event between consecutive ops, on `st`
-    ev.resize(ops.size() + 1);
-    for (auto& e : ev) EO_CHECK_CUDA(cudaEventCreate(&e));
-    EO_CHECK_CUDA(cudaEventRecord(ev[0], st));
-  }
+  // profiling variant: one CUDA event between consecutive ops, on `st`
+  std::vector<cudaEvent_t> ev(ops.size() + 1);
+  for (auto& e : ev) EO_CHECK_CUDA(cudaEventCreate(&e));
+  EO_CHECK_CUDA(cudaEventRecord(ev[0], st));
   int rc = EO_OK;
   for (size_t i = 0; i < ops.size() && !rc; ++i) {
     rc = ops[i].run(B, st);
     if (rc) {
       std::string msg = std::string("op '") + ops[i].name + "': " + get_error();
       set_error("%s", msg.c_str());
-    } else if (ms_per_op) {
+    } else {
       cudaEventRecord(ev[i + 1], st);
     }
   }
-  if (ms_per_op) {
-    if (!rc && cudaEventSynchronize(ev.back()) != cudaSuccess) {
-      set_error("eo_unet_forward_timed: %s", cudaGetErrorString(cudaGetLastError()));
-      rc = EO_ERR_CUDA;
-    }
-    for (size_t i = 0; i < ops.size() && !rc; ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
-    for (auto& e : ev) cudaEventDestroy(e);
+  if (!rc && cudaEventSynchronize(ev.back()) != cudaSuccess) {
+    set_error("eo_unet_forward_timed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = EO_ERR_CUDA;
   }
+  for (size_t i = 0; i < ops.size() && !rc; ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
+  for (auto& e : ev) cudaEventDestroy(e);
   return rc;
+}
+
+// the forward's launches, reading io_* (zeroing of the GroupNorm accumulators included)
+int eo_unet::run_ops(int B, cudaStream_t st) {
+  EO_CHECK_CUDA(cudaMemsetAsync(gn_sums, 0, (size_t)std::max(n_gn, 1) * Bmax * 64 * sizeof(double), st));
+  if (ch_stats_floats) EO_CHECK_CUDA(cudaMemsetAsync(ch_stats, 0, ch_stats_floats * sizeof(double), st));
+  for (size_t i = 0; i < ops.size(); ++i) {
+    int rc = ops[i].run(B, st);
+    if (rc) {
+      std::string msg = std::string("op '") + ops[i].name + "': " + get_error();
+      set_error("%s", msg.c_str());
+      return rc;
+    }
+  }
+  return EO_OK;
+}
+
+// Launch-bound sizes (the reference's 64 x 64, batch 1 case: ~175 launches of a few microseconds of work each):
+// the first call of a shape runs eagerly (lazy packing happens there), the second is captured into a CUDA graph
+// over staging buffers, later ones are four small copies + one graph launch.  *handled = false: run eagerly.
+int eo_unet::forward_graph(const float* x, int Cx, const float* cond, int Cc, const int64_t* t, const int64_t* y,
+                           float* out, int B, cudaStream_t st, bool* handled) {
+  static int graph_mode = -2;
+  if (graph_mode == -2) { const char* e = std::getenv("EO_GRAPH"); graph_mode = e ? atoi(e) : -1; }
+  *handled = false;
+  if (graph_mode == 0 || (graph_mode < 0 && (long long)B * H * W > 65536)) return EO_OK;
+  const long long key = (((long long)B * 64 + Cx) * 64 + Cc) * 2 + (y ? 1 : 0);
+  GraphSlot& g = graphs[key];
+  if (g.failed || ++g.seen == 1) return EO_OK;
+  const size_t hw = (size_t)H * W;
+  if (!gs_x) {
+    int rc;
+    if ((rc = dmalloc(&gs_x, (size_t)Bmax * cfg.in_channels * hw))) return rc;
+    if ((rc = dmalloc(&gs_cond, (size_t)Bmax * cfg.in_channels * hw))) return rc;
+    if ((rc = dmalloc(&gs_out, (size_t)Bmax * cfg.out_channels * hw))) return rc;
+    if ((rc = dmalloc(&gs_t, (size_t)Bmax))) return rc;
+    if ((rc = dmalloc(&gs_y, (size_t)Bmax))) return rc;
+    EO_CHECK_CUDA(cudaStreamCreateWithFlags(&graph_stream, cudaStreamNonBlocking));
+  }
+  if (!g.exec) {
+    io_x = gs_x; io_cx = Cx; io_cond = cond ? gs_cond : nullptr; io_cc = Cc; io_t = gs_t; io_y = y ? gs_y : nullptr; io_out = gs_out;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(graph_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const int rc = run_ops(B, graph_stream);
+      const cudaError_t e = cudaStreamEndCapture(graph_stream, &graph);
+      ok = rc == EO_OK && e == cudaSuccess && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {            // same kernels, launched one by one
+      cudaGetLastError();
+      g.failed = true; g.exec = nullptr;
+      return EO_OK;
+    }
+  }
+  EO_CHECK_CUDA(cudaMemcpyAsync(gs_x, x, (size_t)B * Cx * hw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (cond) EO_CHECK_CUDA(cudaMemcpyAsync(gs_cond, cond, (size_t)B * Cc * hw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  EO_CHECK_CUDA(cudaMemcpyAsync(gs_t, t, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  if (y) EO_CHECK_CUDA(cudaMemcpyAsync(gs_y, y, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  EO_CHECK_CUDA(cudaGraphLaunch(g.exec, st));
+  EO_CHECK_CUDA(cudaMemcpyAsync(out, gs_out, (size_t)B * cfg.out_channels * hw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  *handled = true;
+  return EO_OK;
 }
 
 // ---------------------------------------------------------------------------------------
