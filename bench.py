@@ -41,6 +41,11 @@ WORKLOADS = {
     "c1": dict(size=64, batch=1, desc="64x64 batch 1 (reference notebook case)"),
     "c2": dict(size=128, batch=16, desc="128x128 batch 16"),
     "c3": dict(size=256, batch=64, desc="256x256 batch 64 per GPU"),
+    # secondary configurations of BASELINE.json (not the headline line; `--workload c4|c5`)
+    "c4": dict(size=256, batch=256, kind="ddim", steps_per_image=50,
+               desc="256x256 batch 256 per GPU, DDIM S=50 eta=0 (diffusion/ddim.py)"),
+    "c5": dict(size=256, batch=64, kind="concat", cx=13, cc=15,
+               desc="256x256 batch 64 per GPU, 13-band S2 + 15-channel conditioning concatenated (28 -> 13 ch)"),
 }
 METRIC = "ddpm_T1000_cloud_removal_images_per_sec"
 
@@ -66,13 +71,15 @@ def randomize_zero_init_(model, seed=4321):
     return model
 
 
-def synth_inputs(n, size, seed, device, pin=False):
+def synth_inputs(n, size, seed, device, pin=False, channels=3, cond_channels=0):
     g = torch.Generator().manual_seed(seed)
     gt = torch.rand((n, 3, size, size), generator=g)
     mask = (torch.rand((n, 1, size, size), generator=g) > 0.3).float()
-    x = torch.randn((n, 3, size, size), generator=g)
-    nz = [torch.randn((n, 3, size, size), generator=g) for _ in range(2)]
+    x = torch.randn((n, channels, size, size), generator=g)
+    nz = [torch.randn((n, channels, size, size), generator=g) for _ in range(2)]
     host = dict(gt=gt, mask=mask, x=x, nz0=nz[0], nz1=nz[1])
+    if cond_channels:
+        host["cond"] = torch.rand((n, cond_channels, size, size), generator=g)
     if pin:
         host = {k: v.pin_memory() for k, v in host.items()}
     dev = {k: v.to(device) for k, v in host.items()}
@@ -217,19 +224,48 @@ def run_ours(args, wl):
     _lib.check(L.eo_device_check(), "eo_device_check")
 
     size, B, mode = wl["size"], args.batch or wl["batch"], args.mode
+    kind = wl.get("kind", "sum")
+    steps_per_image = wl.get("steps_per_image", T_DDPM)
+    cx, cc = wl.get("cx", 3), wl.get("cc", 0)
+    arch = dict(ARCH, in_channels=cx + cc, out_channels=cx)
     torch.manual_seed(1234)
-    model = randomize_zero_init_(UNetModel(image_size=size, **ARCH)).to(dev).set_compute_mode(mode)
-    diff = EODiffusion(model, size, 3, timesteps=T_DDPM, cond_type="sum").to(dev)
-    host, d = synth_inputs(B, size, 100 + rank, dev, pin=True)
+    model = randomize_zero_init_(UNetModel(image_size=size, **arch)).to(dev).set_compute_mode(mode)
+    diff = EODiffusion(model, size, cx, timesteps=T_DDPM, cond_type="sum" if kind == "sum" else None).to(dev)
+    host, d = synth_inputs(B, size, 100 + rank, dev, pin=True, channels=cx, cond_channels=cc)
     tab = diff._coef_table(dev)
     ts_rows = diff._timestep_rows(B, dev)
     hw = size * size
     nz = [d["nz0"], d["nz1"]]
     x = d["x"].clone()
     stream = _lib.stream_ptr
+    sampler = None
+    if kind == "ddim":
+        from eo_diffusion_b200 import DDIMSampler
+        sampler = DDIMSampler(diff)
+        sampler.make_schedule(ddim_num_steps=steps_per_image, ddim_eta=0.0, verbose=False)
+        ddim_ts = [int(v) for v in sampler.ddim_timesteps]
+        scal = []
+        for idx in range(len(ddim_ts)):            # the scalars DDIMSampler.p_sample_ddim hands to eo_ddim_step
+            a_t, a_prev = float(sampler.ddim_alphas[idx]), float(sampler.ddim_alphas_prev[idx])
+            sg = float(sampler.ddim_sigmas[idx])
+            scal.append((math.sqrt(a_t), float(sampler.ddim_sqrt_one_minus_alphas[idx]), math.sqrt(a_prev),
+                         math.sqrt(max(1. - a_prev - sg * sg, 0.)), sg))
+        pred_x0 = torch.empty_like(x)
 
     def device_step(k):
+        if kind == "ddim":
+            idx = len(ddim_ts) - 1 - (k % len(ddim_ts))
+            pred = model(x, ts_rows[ddim_ts[idx]])
+            sa, s1, sp, dc, sg = scal[idx]
+            _lib.check(L.eo_ddim_step(_lib.ptr(x), _lib.ptr(pred), None, _lib.ptr(x), _lib.ptr(pred_x0), sa, s1, sp, dc,
+                                      sg, 1.0, x.numel(), stream()), "eo_ddim_step")
+            return
         i = T_DDPM - 1 - (k % (T_DDPM - 1))           # i >= 1
+        if kind == "concat":
+            pred = model(x, ts_rows[i], cond=d["cond"])
+            _lib.check(L.eo_ddpm_step(_lib.ptr(x), _lib.ptr(pred), _lib.ptr(nz[k % 2]), _lib.ptr(ts_rows[i]), _lib.ptr(tab),
+                                      _lib.ptr(x), B, cx, hw, 1, 1, stream()), "eo_ddpm_step")
+            return
         pred = model(x, ts_rows[i])
         _lib.check(L.eo_ddpm_step_mix(_lib.ptr(x), _lib.ptr(pred), _lib.ptr(nz[k % 2]), _lib.ptr(ts_rows[i]),
                                       _lib.ptr(d["gt"]), _lib.ptr(d["mask"]), _lib.ptr(nz[(k + 1) % 2]),
@@ -251,8 +287,9 @@ def run_ours(args, wl):
         return float(t.item())
 
     # ---- device-resident steps ------------------------------------------------------------
-    _lib.check(L.eo_ddpm_sum_mix(_lib.ptr(x), _lib.ptr(d["gt"]), _lib.ptr(d["mask"]), _lib.ptr(nz[0]),
-                                 _lib.ptr(ts_rows[T_DDPM - 1]), _lib.ptr(tab), _lib.ptr(x), B, 3, hw, stream()))
+    if kind == "sum":
+        _lib.check(L.eo_ddpm_sum_mix(_lib.ptr(x), _lib.ptr(d["gt"]), _lib.ptr(d["mask"]), _lib.ptr(nz[0]),
+                                     _lib.ptr(ts_rows[T_DDPM - 1]), _lib.ptr(tab), _lib.ptr(x), B, 3, hw, stream()))
     for k in range(args.warmup):
         device_step(k)
     barrier()
@@ -266,7 +303,7 @@ def run_ours(args, wl):
     barrier()
     clk = clocks.finish()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    value = world * B / (T_DDPM * ms_step * 1e-3)
+    value = world * B / (steps_per_image * ms_step * 1e-3)
     assert bool(torch.isfinite(x).all()), "sampler state diverged"
     launches_step = model.launches_per_forward() + 1
 
@@ -275,19 +312,34 @@ def run_ours(args, wl):
     out_host = torch.empty_like(hx).pin_memory()
     dx, dn, dgt, dm = (torch.empty_like(d["x"]), torch.empty_like(d["x"]), torch.empty_like(d["gt"]),
                        torch.empty_like(d["mask"]))
-    h2d = sum(t.numel() * 4 for t in (hx, host["nz0"], host["gt"], host["mask"]))
+    dcond = torch.empty_like(d["cond"]) if kind == "concat" else None
+    if kind == "sum":
+        h2d = sum(t.numel() * 4 for t in (hx, host["nz0"], host["gt"], host["mask"]))
+    elif kind == "concat":
+        h2d = sum(t.numel() * 4 for t in (hx, host["nz0"], host["cond"]))
+    else:
+        h2d = hx.numel() * 4
     d2h = out_host.numel() * 4
 
     def e2e_step(k):
-        i = T_DDPM - 1 - (k % (T_DDPM - 1))
         dx.copy_(hx, non_blocking=True)
+        if kind == "ddim":
+            idx = len(ddim_ts) - 1 - (k % len(ddim_ts))
+            nxt, _ = sampler.p_sample_ddim(dx, None, ts_rows[ddim_ts[idx]], index=idx)   # public method: UNet + DDIM update
+            out_host.copy_(nxt, non_blocking=True)
+            return
+        i = T_DDPM - 1 - (k % (T_DDPM - 1))
         dn.copy_(host["nz0"] if k % 2 == 0 else host["nz1"], non_blocking=True)
-        dgt.copy_(host["gt"], non_blocking=True)
-        dm.copy_(host["mask"], non_blocking=True)
         t = ts_rows[i]
-        _lib.check(L.eo_ddpm_sum_mix(_lib.ptr(dx), _lib.ptr(dgt), _lib.ptr(dm), _lib.ptr(dn), _lib.ptr(t),
-                                     _lib.ptr(tab), _lib.ptr(dx), B, 3, hw, stream()))
-        nxt = diff._reverse_diffusion_with_clip(dx, t, dn)      # public method: UNet + posterior
+        if kind == "concat":
+            dcond.copy_(host["cond"], non_blocking=True)
+            nxt = diff._reverse_diffusion_with_clip(dx, t, dn, cond=dcond)
+        else:
+            dgt.copy_(host["gt"], non_blocking=True)
+            dm.copy_(host["mask"], non_blocking=True)
+            _lib.check(L.eo_ddpm_sum_mix(_lib.ptr(dx), _lib.ptr(dgt), _lib.ptr(dm), _lib.ptr(dn), _lib.ptr(t),
+                                         _lib.ptr(tab), _lib.ptr(dx), B, 3, hw, stream()))
+            nxt = diff._reverse_diffusion_with_clip(dx, t, dn)      # public method: UNet + posterior
         out_host.copy_(nxt, non_blocking=True)
 
     n_e2e = max(2, min(args.steps, 5))
@@ -299,7 +351,7 @@ def run_ours(args, wl):
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1) / n_e2e)
-    e2e_value = world * B / (T_DDPM * ms_e2e * 1e-3)
+    e2e_value = world * B / (steps_per_image * ms_e2e * 1e-3)
 
     # ---- roofline of the dominant kernel family, timed per op with CUDA events --------------
     roofline = None
@@ -308,9 +360,10 @@ def run_ours(args, wl):
         h = C.c_void_p(model._handle)
         nops = L.eo_unet_num_ops(h)
         ms = (C.c_float * nops)()
-        eps = torch.empty((B, 3, size, size), device=dev)
+        eps = torch.empty((B, cx, size, size), device=dev)
+        cond_p = _lib.ptr(d["cond"]) if kind == "concat" else None
         for _ in range(2):   # second pass is the warm one
-            _lib.check(L.eo_unet_forward_timed(h, _lib.ptr(x), 3, None, 0, _lib.ptr(ts_rows[500]), None,
+            _lib.check(L.eo_unet_forward_timed(h, _lib.ptr(x), cx, cond_p, cc, _lib.ptr(ts_rows[500]), None,
                                                _lib.ptr(eps), B, stream(), ms), "eo_unet_forward_timed")
         name, kern, fl, by = C.c_char_p(), C.c_char_p(), C.c_double(), C.c_double()
         for i in range(nops):
@@ -349,7 +402,7 @@ def run_ours(args, wl):
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and kind == "sum":
         sample_b, sample_steps = 1, 2
         sec = cpu_reference_steps(size, sample_b, sample_steps, 1)
         cpu = {"value": sample_b / (T_DDPM * sec), "unit": "images/s", "cores": torch.get_num_threads(),
@@ -360,7 +413,7 @@ def run_ours(args, wl):
     if world > 1:
         # the one collective of the path: gather the final images of all ranks
         import torch.distributed as dist
-        gathered = torch.empty((world * B, 3, size, size), device=dev)
+        gathered = torch.empty((world * B, cx, size, size), device=dev)
         dist.all_gather_into_tensor(gathered, x)
         torch.cuda.synchronize()
         dist.destroy_process_group()
@@ -368,11 +421,15 @@ def run_ours(args, wl):
     if rank == 0:
         flops_img = sum(v["flops"] for v in breakdown.values()) / B if breakdown else None
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if kind != "ddim" else f"ddim_S{steps_per_image}_images_per_sec", "value": value,
+            "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": mode, "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wl['desc']}, DDPM T={T_DDPM}, cond 'sum' (3+3->3 ch), "
-                                   "clipped posterior, UNet base 128 mult [1,2,3,4] attn [4,8] 2 res blocks 8 heads",
+            "config": {"workload": f"{args.workload}: {wl['desc']}, "
+                                   + ("DDIM" if kind == "ddim" else f"DDPM T={T_DDPM}, "
+                                      + ("cond 'sum' (3+3->3 ch), " if kind == "sum" else "cond concatenated, ")
+                                      + "clipped posterior")
+                                   + ", UNet base 128 mult [1,2,3,4] attn [4,8] 2 res blocks 8 heads",
                        "batch_per_gpu": B, "image": size, "parallelism": f"batch-sharded x{world}",
                        "l2": "activations per step (GBs) exceed the 126 MB L2; no flush needed"
                              if B * size * size * 128 * 2 > 4 * 126e6 else

@@ -950,6 +950,23 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
                            -1, nullptr, H, W, &h, st, true, nullptr, 2.0 * H * W * L0.cout * 9 * cin)))
       return rc;
     free_act(col);
+  } else if (mode == EO_MODE_BF16 && tc_ends && tc_conv3_enabled() && 2 * L0.cin <= 64 && L0.cout % 64 == 0) {
+    // up to 32 input channels (the multispectral concat configuration: 13 + 15): the input becomes one 64-channel
+    // bf16 NHWC block (values + rounding residuals) and the stem an ordinary 3x3 tensor-core convolution
+    Act xin = new_act(64, H, W);
+    const int cin = L0.cin;
+    push("input_blocks.0.nhwc", [=](int B, cudaStream_t s) -> int {
+      if (io_cx + io_cc != cin) { set_error("stem: %d + %d input channels, expected %d", io_cx, io_cc, cin); return EO_ERR_ARG; }
+      return launch_stem_nhwc(io_x, io_cx, io_cond, io_cc, ptr(xin.off), B, H, W, s);
+    });
+    note("k_stem_nhwc", 0, (double)H * W * (64 * 2 + cin * 4));
+    float* w2 = nullptr;
+    if ((rc = dmalloc(&w2, (size_t)L0.cout * 64 * 9))) return rc;
+    if ((rc = launch_stem_weight3(w(L0.prefix + "weight"), L0.cout, cin, w2, st))) return rc;
+    if ((rc = plan_conv_tc("input_blocks.0", {seg3x3(xin)}, {{w2, 64, 3, 0, 64}}, L0.cout, nullptr, w(L0.prefix + "bias"), nullptr,
+                           -1, nullptr, H, W, &h, st, true, nullptr, 2.0 * H * W * L0.cout * 9 * cin)))
+      return rc;
+    free_act(xin);
   } else
   {
     const Layer& L = in_blocks[0].layers[0];

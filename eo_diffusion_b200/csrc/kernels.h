@@ -112,6 +112,10 @@ int launch_space_to_depth(const void* src, void* dst, int B, int Bstride, int H,
 // channels (tap, c) rounded to bf16 then their rounding residuals; and the matching [Cout][64] fp32 weights
 int launch_stem_im2col(const float* x, int Cx, const float* cond, int Cc, void* dst, int B, int H, int W, cudaStream_t st);
 int launch_stem_weight(const float* w, int Cout, int C, float* w2, cudaStream_t st);
+// 4..32 input channels: cat(x, cond) -> 64-channel bf16 NHWC pixels (values, then rounding residuals) and the
+// matching [Cout][64][3][3] fp32 weights; the stem is then a plain 3x3 tensor-core conv
+int launch_stem_nhwc(const float* x, int Cx, const float* cond, int Cc, void* dst, int B, int H, int W, cudaStream_t st);
+int launch_stem_weight3(const float* w, int Cout, int C, float* w2, cudaStream_t st);
 // tensor-core head: the first C of `ld` channels of a bf16 NHWC tensor -> NCHW fp32
 int launch_head_to_nchw(const void* src_bf16, int ld, float* dst, int B, int HW, int C, cudaStream_t st);
 // generic NHWC (dt) -> NCHW fp32 copy, for eo_unet_read_activation

@@ -1003,6 +1003,36 @@ k_stem_im2col(const float* __restrict__ x, int Cx, const float* __restrict__ con
     for (int j = 0; j < 8; ++j) o[j] = reinterpret_cast<const uint4*>(e)[j];
   }
 }
+// 4..32 input channels: cat(x, cond) (NCHW fp32) -> one 64-channel bf16 NHWC pixel, channels [0, C) the values
+// rounded to bf16, [C, 2C) their rounding residuals, rest zero; the stem is then an ordinary 3x3 tensor-core conv
+__global__ void __launch_bounds__(256)
+k_stem_nhwc(const float* __restrict__ x, int Cx, const float* __restrict__ cond, int Cc, __nv_bfloat16* __restrict__ dst,
+            long long HW, long long npix) {
+  const int C = Cx + Cc;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+    const long long b = pix / HW, r = pix - b * HW;
+    __align__(16) __nv_bfloat16 e[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) e[k] = __float2bfloat16_rn(0.f);
+    for (int c = 0; c < C; ++c) {
+      const float v = c < Cx ? __ldg(x + (b * Cx + c) * HW + r) : __ldg(cond + (b * Cc + (c - Cx)) * HW + r);
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      e[c] = hi;
+      e[C + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + pix * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = reinterpret_cast<const uint4*>(e)[j];
+  }
+}
+// w [Cout][C][3][3] -> w2 [Cout][64][3][3] matching k_stem_nhwc's channel order
+__global__ void k_stem_weight3(const float* __restrict__ w, int Cout, int C, float* __restrict__ w2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 64 * 9) return;
+  const int tap = i % 9, c = (i / 9) & 63, n = i / (9 * 64);
+  const int cs = c < C ? c : c - C;
+  w2[i] = c < 2 * C ? w[((long long)n * C + cs) * 9 + tap] : 0.f;
+}
 // w [Cout][C][3][3] -> w2 [Cout][64] matching k_stem_im2col's channel order
 __global__ void k_stem_weight(const float* __restrict__ w, int Cout, int C, float* __restrict__ w2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1041,6 +1071,18 @@ int launch_stem_im2col(const float* x, int Cx, const float* cond, int Cc, void* 
     case 2: k_stem_im2col<2><<<ew_grid(npix), 256, 0, st>>>(x, Cx, cond, Cc, d, H, W, npix); break;
     default: k_stem_im2col<3><<<ew_grid(npix), 256, 0, st>>>(x, Cx, cond, Cc, d, H, W, npix); break;
   }
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+int launch_stem_nhwc(const float* x, int Cx, const float* cond, int Cc, void* dst, int B, int H, int W, cudaStream_t st) {
+  EO_REQUIRE(2 * (Cx + Cc) <= 64, EO_ERR_ARG, "stem_nhwc: %d input channels do not fit one 64-channel block", Cx + Cc);
+  const long long npix = (long long)B * H * W;
+  k_stem_nhwc<<<ew_grid(npix), 256, 0, st>>>(x, Cx, cond, Cc, reinterpret_cast<__nv_bfloat16*>(dst), (long long)H * W, npix);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+int launch_stem_weight3(const float* w, int Cout, int C, float* w2, cudaStream_t st) {
+  k_stem_weight3<<<ceil_div(Cout * 64 * 9, 256), 256, 0, st>>>(w, Cout, C, w2);
   EO_CHECK_LAUNCH();
   return EO_OK;
 }
