@@ -1375,6 +1375,7 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
   }
   TcConvPlan* plan = nullptr;
   float* gn_buf = nullptr;
+  double* stats_buf = nullptr;
   if (!rc) {
     TcConvParams p;
     p.nseg = 1;
@@ -1399,6 +1400,13 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
     }
     p.B = B; p.H = H; p.W = W; p.Wp = Wp; p.Ktot = K; p.Cout = Cout; p.bias = bias;
     p.residual = residual; p.out = y_bf16;
+    // development aid (tools/conv3_trace.py): EO_TEST_STATS=1 also emits the fused GroupNorm statistics
+    const char* tsx = std::getenv("EO_TEST_STATS");
+    if (tsx && tsx[0] == '1' && tc_conv_stats_supported(H, W)) {
+      EO_CHECK_CUDA(cudaMalloc(&stats_buf, (size_t)B * Cout * 2 * sizeof(double)));
+      EO_CHECK_CUDA(cudaMemsetAsync(stats_buf, 0, (size_t)B * Cout * 2 * sizeof(double), st));
+      p.stats = stats_buf;
+    }
     rc = tc_conv_plan_create(p, &plan);
   }
   if (!rc) rc = tc_conv_launch(plan, B, st);
@@ -1406,6 +1414,7 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
   tc_conv_plan_destroy(plan);
   cudaFree(Wp);
   if (gn_buf) cudaFree(gn_buf);
+  if (stats_buf) cudaFree(stats_buf);
   if (!rc && e != cudaSuccess) { set_error("eo_test_conv_tc: %s", cudaGetErrorString(e)); rc = EO_ERR_CUDA; }
   return rc;
 }

@@ -68,7 +68,8 @@ struct Smem {
   static constexpr int STG_OFF = 0;                                    // 2 staging tiles
   static constexpr int TAB_OFF = STG_OFF + 2 * STG_BYTES;
   static constexpr int STAT_OFF = TAB_OFF + MAX_ENT * (int)sizeof(KEnt3);   // [4 warps][256][2] floats
-  static constexpr int BAR_OFF = STAT_OFF + 4 * 256 * 2 * 4;
+  static constexpr int WB_OFF = STAT_OFF + 4 * 256 * 2 * 4;            // [8 epilogue warps][2 chunks][64] floats: bias + timestep row
+  static constexpr int BAR_OFF = WB_OFF + 8 * 128 * 4;
   // r_full r_empty g_ready g_empty [SA_MAX each] b_full[MAX_SB] b_empty[MAX_SB] tmem_full[2] tmem_empty[2]
   // res_full[2] res_empty[2]
   static constexpr int NBAR = 4 * SA_MAX + 2 * MAX_SB + 8;
@@ -93,6 +94,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
       "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
       :: "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// pull one TMA box into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               :: "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -193,8 +199,8 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_ptr;
 
   // 640 threads leave 96 registers each (61440 for the CTA); the epilogue warps need more and the issue
-  // warps far fewer: warpgroup 0 drops to 40, the transform warpgroups to 88, the epilogue warpgroups
-  // grow to 128 (40 + 2*128 + 2*88 = 472 <= 480 = 5 * 96: setmaxnreg.inc can always be satisfied)
+  // warps far fewer: warpgroup 0 drops to 40, the epilogue warpgroups grow to 104, the transform warpgroups
+  // (two patches of operand data in registers) to 112 (40 + 2*104 + 2*112 = 472 <= 480 = 5 * 96)
 
   // Producer and MMA warps: the WHOLE warp walks the loops (warp-uniform control flow keeps addresses,
   // coordinates and descriptors in uniform registers) and one elected lane issues.  Under
@@ -222,6 +228,13 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           // one arrival per phase: the leader's producer, which posts the byte count of BOTH CTAs' loads
           if (rank == 0) tc::mbar_arrive_expect_tx(&r_full[ra.i], 2 * bytes);
           tc::tma2_load_4d(dst, ma, r_full_l + ra.i * 8, en.c0, cw, chh, t.n0 + en.dn);
+        }
+        // a GroupNorm-folded patch is fetched by the transform warps with plain loads, one patch ahead of the
+        // tensor pipe: too late to hide an HBM miss (measured: 2340 clk per patch, 1300 of them load latency).
+        // Pull the SAME entry's patch of this CTA's NEXT tile into L2 now, a whole tile ahead.
+        if (en.gn && w + ncl < n_work && tc::elect_one()) {
+          const Tile tn = decode_tile(w + ncl, n_ntiles, rank, g, BN);
+          if (tn.n0 < B) tma_prefetch_4d(ma, en.c0, tn.w0 - 1, tn.h0 - 1, tn.n0 + en.dn);
         }
         __syncwarp();
         if (!en.gn) ra.next((uint32_t)SAR);
@@ -338,7 +351,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       }
     }
   } else if (warp >= XF_WARP0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ------------------------------------------------------------------ operand transform
     // GroupNorm affine (+ SiLU) of the activation, applied in place to the stage TMA just filled
     // (reference: normalization / nn.SiLU in front of every conv, unet_openai.py:313-316, :337-342,
@@ -378,8 +391,11 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         if (tab[c.e].gn) { c.valid = true; return; }
       }
     };
-    // one patch = 6 x 16 bytes per thread in registers
-    uint4 buf[XF_PIX];
+    // two patches of 6 x 16 bytes per thread in registers: the loads of patch i+1 are issued BEFORE patch i is
+    // transformed (a first version issued them after the hand-over, because fence.proxy.async waits for every
+    // load the thread has in flight: the patch then cost its full load latency, 2340 clk against 1000 of
+    // arithmetic; issued a whole transform earlier they have landed by the time the fence is reached)
+    uint4 bufa[XF_PIX], bufb[XF_PIX];
     float4 na0, na1, nb0, nb1;                 // scale / shift of the next patch
     na0 = na1 = nb0 = nb1 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto edges_of = [&](const Tile& t) -> uint32_t {   // image borders the tile touches (+ "beyond the patch")
@@ -403,20 +419,18 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       nb0 = __ldg(reinterpret_cast<const float4*>(gsh + o));
       nb1 = __ldg(reinterpret_cast<const float4*>(gsh + o + 4));
     };
-    Cur cur{cid, 0, Ring(), Tile(), false};
-    seek(cur, true);
-    if (cur.valid) {
-      const KEnt3 en = tab[cur.e];
+    auto load_patch = [&](const Cur& c, uint4 (&buf)[XF_PIX]) {
+      const KEnt3 en = tab[c.e];
       int Cs;
-      const uint8_t* src = src_of(cur, en, Cs);
-      const uint32_t te = cur.t.n0 < B ? edges_of(cur.t) : 0xffffffffu;
-      load_affine(cur, en);
+      const uint8_t* src = src_of(c, en, Cs);
+      const uint32_t te = c.t.n0 < B ? edges_of(c.t) : 0xffffffffu;
 #pragma unroll
       for (int i = 0; i < XF_PIX; ++i)
         if (!(ptab[i] & te)) buf[i] = __ldg(reinterpret_cast<const uint4*>(src + (long long)plin[i] * Cs * 2));
-    }
+    };
     long long tr_xb = 0;
-    while (cur.valid) {
+    // transform the patch in `buf` (cursor `cur`) while the loads of the next one (`nxt`) are in flight in `bufn`
+    auto step = [&](Cur& cur, uint4 (&buf)[XF_PIX], uint4 (&bufn)[XF_PIX]) {
       const KEnt3 en = tab[cur.e];
       const bool silu = en.gn == 2;
       const uint32_t te = cur.t.n0 < B ? edges_of(cur.t) : 0xffffffffu;
@@ -429,14 +443,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       const float4 b1 = make_float4(nb1.x * hf, nb1.y * hf, nb1.z * hf, nb1.w * hf);
       Cur nxt = cur;
       seek(nxt, false);
-      KEnt3 en2 = en;
-      int Cs2 = 0;
-      const uint8_t* src2 = nullptr;
-      uint32_t te2 = 0xffffffffu;
       if (nxt.valid) {
-        en2 = tab[nxt.e];
-        src2 = src_of(nxt, en2, Cs2);
-        if (nxt.t.n0 < B) te2 = edges_of(nxt.t);
+        load_affine(nxt, tab[nxt.e]);
+        load_patch(nxt, bufn);
       }
       tc::mbar_wait(&g_empty[cur.ring.i], cur.ring.ph ^ 1);       // the MMAs that read this stage have retired
       const long long t_b0 = TRACE ? clock64() : 0;
@@ -456,43 +465,43 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         __nv_bfloat162 o = __floats2bfloat162_rn(x0, x1);
         return *reinterpret_cast<uint32_t*>(&o);
       };
-      auto run = [&](auto act_tag) {
-        constexpr bool ACT = decltype(act_tag)::value;
+      // (one copy of this body: the kernel's warp roles already crowd the instruction cache -- with the
+      // loop duplicated per activation flag and per register buffer the epilogue warps stalled on fetches)
 #pragma unroll
-        for (int i = 0; i < XF_PIX; ++i) {
-          if (ptab[i] & (16u << 16)) continue;                    // beyond the patch (only the last i)
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          const bool in_img = !(ptab[i] & te);
-          if (in_img) v = buf[i];
-          if (in_img) {
-            v.x = xf2(v.x, a0.x, b0.x, a0.y, b0.y, ACT);
-            v.y = xf2(v.y, a0.z, b0.z, a0.w, b0.w, ACT);
-            v.z = xf2(v.z, a1.x, b1.x, a1.y, b1.y, ACT);
-            v.w = xf2(v.w, a1.z, b1.z, a1.w, b1.w, ACT);
-          }
-          *reinterpret_cast<uint4*>(st + (ptab[i] & 0xffffu)) = v;    // zeros outside the image
+      for (int i = 0; i < XF_PIX; ++i) {
+        if (ptab[i] & (16u << 16)) continue;                    // beyond the patch (only the last i)
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        const bool in_img = !(ptab[i] & te);
+        if (in_img) v = buf[i];
+        if (in_img) {
+          v.x = xf2(v.x, a0.x, b0.x, a0.y, b0.y, silu);
+          v.y = xf2(v.y, a0.z, b0.z, a0.w, b0.w, silu);
+          v.z = xf2(v.z, a1.x, b1.x, a1.y, b1.y, silu);
+          v.w = xf2(v.w, a1.z, b1.z, a1.w, b1.w, silu);
         }
-      };
-      if (silu) run(std::true_type{}); else run(std::false_type{});
+        *reinterpret_cast<uint4*>(st + (ptab[i] & 0xffffu)) = v;    // zeros outside the image
+      }
       tc::fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's operand reads
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_remote(g_ready_l + cur.ring.i * 8);
       if (TRACE) tr_xb += clock64() - t_b0;
-      // the next patch's loads go out only now: a fence waits for every load the thread has in flight, so
-      // loads issued before it would serialise on their own latency.  They arrive while this thread waits
-      // for the MMA warp to release the next stage (it runs up to two stages ahead of the tensor pipe).
-      if (nxt.valid) {
-        load_affine(nxt, en2);
-#pragma unroll
-        for (int i = 0; i < XF_PIX; ++i)
-          if (!(ptab[i] & te2)) buf[i] = __ldg(reinterpret_cast<const uint4*>(src2 + (long long)plin[i] * Cs2 * 2));
-      }
       cur = nxt;
+    };
+    Cur cur{cid, 0, Ring(), Tile(), false};
+    seek(cur, true);
+    if (cur.valid) {
+      load_affine(cur, tab[cur.e]);
+      load_patch(cur, bufa);
+    }
+    while (cur.valid) {
+      step(cur, bufa, bufb);
+#pragma unroll
+      for (int i = 0; i < XF_PIX; ++i) bufa[i] = bufb[i];
     }
     if (TRACE && xt == 0) trace_put(ep, 7, tr_xb);
 #undef EO_LOAD_AFFINE
   } else if (warp >= EPI_WARP0) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ------------------------------------------------------------------ epilogue
     // Two sets of four warps (one warp per TMEM lane quadrant in each); set s takes the 64-channel
     // chunks c = s, s+2, ... of every tile.  A warp owns 32 accumulator rows end to end: TMEM ->
@@ -518,9 +527,29 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const uint32_t tmem_empty_leader = tc::mapa_u32(tc::smem_u32(&tmem_empty[0]), 0);
     uint32_t it = 0, res_uses = 0;
     long long tr_wait = 0, tr_busy = 0;
+    // Tiles inside one image (every halo-patch grid): bias[n] + bias_nc[image][n] of this warp's channels sit in a
+    // warp-private shared-memory row, rebuilt only when the image or the channel tile changes -- the 16 global
+    // loads per 32 columns they replace cost an L2 round trip each time (the L1 is all shared memory here).
+    float* wb = reinterpret_cast<float*>(smem + Smem::WB_OFF) + ew * 128;
+    const bool cache_bias = single_image && (ep.bias || ep.bias_nc);
+    int wb_img = -1, wb_nbase = -1;
     for (int w = cid; w < n_work; w += ncl, ++it) {
       const Tile t = decode_tile(w, n_ntiles, rank, g, BN);
       const int n_img = t.n0 + nn;
+      if (cache_bias && t.n0 < B && (t.n0 != wb_img || t.nbase != wb_nbase)) {
+        __syncwarp();
+        for (int slot = 0, c = set; c < nchunks; c += 2, ++slot) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int n = t.nbase + c * 64 + hh * 32 + lane;
+            float v = ep.bias ? __ldg(ep.bias + n) : 0.f;
+            if (ep.bias_nc) v += __ldg(ep.bias_nc + (long long)t.n0 * ep.ld_bias_nc + n);
+            wb[slot * 64 + hh * 32 + lane] = v;
+          }
+        }
+        wb_img = t.n0; wb_nbase = t.nbase;
+        __syncwarp();
+      }
       const bool valid = n_img < B;
       const bool warp_valid = __shfl_sync(0xffffffffu, valid ? 1 : 0, 0) != 0;
       const float* bnc = (ep.bias_nc && valid) ? ep.bias_nc + (long long)n_img * ep.ld_bias_nc : nullptr;
@@ -540,8 +569,8 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         // the TMA store this warp issued from its staging rows one chunk ago has read them out
         if (lane == 0) bulk_wait_read0();      // (bulk groups belong to the issuing thread: always lane 0)
         __syncwarp();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {       // not unrolled: instruction-cache footprint
           const int n = t.nbase + c * 64 + half * 32;
           float f[32];
           {
@@ -556,14 +585,23 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster_relaxed(tmem_empty_leader + ab * 8);
           }
-          if (ep.bias) {
+          if (cache_bias) {
+            if (valid) {
+              const float* wr = wb + ((c - set) >> 1) * 64 + half * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(wr + j);
+                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+              }
+            }
+          } else if (ep.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
               f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
             }
           }
-          if (bnc) {
+          if (bnc && !cache_bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(bnc + n + j));

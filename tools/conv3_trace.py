@@ -1,0 +1,55 @@
+"""Development tool: per-CTA phase totals of the persistent tensor-core convolution (tc_conv3.cu) on a B200.
+Slots (eo_debug_conv_trace): 0 lifetime, 1 MMA warp waits on operands, 2 MMA warp waits on a free accumulator
+(= the epilogue is behind), 3 epilogue waits on the accumulator (= the main loop is behind), 4 epilogue busy,
+5 producer waits on free stages, 6 tiles, 7 transform warps busy.  All in clk, printed per tile.
+usage: [EO_TEST_GN=2] [EO_TEST_STATS=1] python tools/conv3_trace.py [B H W Cin Cout k res]"""
+import math
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from eo_diffusion_b200 import _lib  # noqa: E402
+
+
+def run(B, H, W, Cin, Cout, k, res):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((B, H, W, Cin), generator=g).to(dev).to(torch.bfloat16)
+    w = (torch.randn((Cout, Cin, k, k), generator=g) / math.sqrt(Cin * k * k)).to(dev)
+    b = torch.randn((Cout,), generator=g).to(dev)
+    r = torch.randn((B, H, W, Cout), generator=g).to(dev).to(torch.bfloat16) if res else None
+    y = torch.empty((B, H, W, Cout), dtype=torch.bfloat16, device=dev)
+    L = _lib.lib()
+    call = lambda: _lib.check(L.eo_test_conv_tc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(r), _lib.ptr(y),
+                                                B, H, W, Cin, Cout, k, _lib.stream_ptr()), "conv")
+    call()
+    torch.cuda.synchronize()
+    tr = torch.zeros((148, 8), dtype=torch.int64, device=dev)
+    L.eo_debug_conv_trace(_lib.ptr(tr), 148)
+    call()
+    torch.cuda.synchronize()
+    L.eo_debug_conv_trace(None, 0)
+    t = tr.cpu().numpy()
+    lead = t[t[:, 6] > 0]                       # leader CTAs carry the MMA warp's tile count
+    tiles = np.median(lead[:, 6])
+    f = lambda a, c: np.median(a[:, c]) / tiles
+    allc = t[t[:, 0] > 0]
+    flops = 2.0 * B * H * W * Cout * Cin * k * k
+    print(f"conv B={B} {H}x{W} {Cin}->{Cout} k={k} res={res}: {tiles:.0f} tiles per CTA pair, {f(allc, 0):.0f} clk per tile "
+          f"(MMA floor {Cin * k * k / 64 * (256 if Cout % 256 else 512) / (1 if Cout % 256 else 1):.0f})\n"
+          f"   per tile: MMA waits operands {f(lead, 1):.0f}, MMA waits accumulator {f(lead, 2):.0f}; epilogue waits accumulator "
+          f"{f(allc, 3):.0f}, epilogue busy {f(allc, 4):.0f}; producer waits stages {f(lead, 5):.0f}; transform busy {f(allc, 7):.0f}")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        a = [int(v) for v in sys.argv[1:8]]
+        run(*a[:6], bool(a[6]) if len(a) > 6 else False)
+    else:
+        run(64, 256, 256, 128, 128, 3, False)
+        run(64, 256, 256, 128, 128, 3, True)
+        run(64, 256, 256, 64, 128, 1, False)
+        run(64, 64, 64, 384, 384, 1, True)
+        run(64, 128, 128, 256, 256, 3, False)
