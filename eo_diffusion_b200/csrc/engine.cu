@@ -92,6 +92,7 @@ struct Layer {
   std::string prefix;   // e.g. "input_blocks.1.0."
   int cin = 0, cout = 0, heads = 0;
   int tb_off = -1;      // ResBlock: column offset into the per-step embedding table
+  int updown = 0;       // ResBlock of resblock_updown: 1 = down (2x2 average), 2 = up (nearest x2)
 };
 struct Block { std::vector<Layer> layers; std::string name; };
 
@@ -192,12 +193,13 @@ struct eo_unet {
     const std::string& p = L.prefix;
     add_w(p + "in_layers.0.weight", {L.cin}); add_w(p + "in_layers.0.bias", {L.cin});
     add_conv_w(p + "in_layers.2.", L.cout, L.cin, 3);
-    add_w(p + "emb_layers.1.weight", {L.cout, ted}); add_w(p + "emb_layers.1.bias", {L.cout});
+    const int erows = (cfg.use_scale_shift_norm ? 2 : 1) * L.cout;      // FiLM: (scale | shift)
+    add_w(p + "emb_layers.1.weight", {erows, ted}); add_w(p + "emb_layers.1.bias", {erows});
     add_w(p + "out_layers.0.weight", {L.cout}); add_w(p + "out_layers.0.bias", {L.cout});
     add_conv_w(p + "out_layers.3.", L.cout, L.cout, 3);
     if (L.cin != L.cout) add_conv_w(p + "skip_connection.", L.cout, L.cin, 1);
     L.tb_off = tb_total;
-    tb_total += L.cout;
+    tb_total += erows;
   }
   void add_attn_w(Layer& L) {
     const std::string& p = L.prefix;
@@ -243,8 +245,9 @@ struct eo_unet {
       }
       if (level != c.n_channel_mult - 1) {
         Block b; b.name = "input_blocks." + std::to_string(in_blocks.size());
-        Layer L; L.kind = L_DOWN; L.prefix = b.name + ".0."; L.cin = L.cout = ch;
-        add_conv_w(L.prefix + "op.", ch, ch, 3);
+        Layer L; L.prefix = b.name + ".0."; L.cin = L.cout = ch;
+        if (c.resblock_updown) { L.kind = L_RES; L.updown = 1; add_res_w(L); }       // unet_openai.py:645-658
+        else { L.kind = L_DOWN; add_conv_w(L.prefix + "op.", ch, ch, 3); }
         b.layers.push_back(L); in_blocks.push_back(b); chans.push_back(ch);
         ds *= 2;
       }
@@ -270,8 +273,9 @@ struct eo_unet {
           add_attn_w(A); b.layers.push_back(A);
         }
         if (level && i == c.num_res_blocks) {
-          Layer U; U.kind = L_UP; U.prefix = b.name + "." + std::to_string(li++) + "."; U.cin = U.cout = ch;
-          add_conv_w(U.prefix + "conv.", ch, ch, 3);
+          Layer U; U.prefix = b.name + "." + std::to_string(li++) + "."; U.cin = U.cout = ch;
+          if (c.resblock_updown) { U.kind = L_RES; U.updown = 2; add_res_w(U); }     // unet_openai.py:722-735
+          else { U.kind = L_UP; add_conv_w(U.prefix + "conv.", ch, ch, 3); }
           b.layers.push_back(U);
           ds /= 2;
         }
@@ -575,8 +579,114 @@ struct eo_unet {
     return o;
   }
 
+  // ResBlock._forward for the variants of the reference's UNet / UNetBig / UNetSmall factories: scale-shift (FiLM)
+  // conditioning (unet_openai.py:377-381) and up/down-sampling blocks (:366-371).  SiLU(GroupNorm(x)) is
+  // materialised (resampled for an up/down block, like x itself), the first convolution reads it plainly; the second
+  // GroupNorm's folded affine is modulated by the block's (scale | shift) row before it rides on the second conv.
+  int plan_res_x(const Layer& L, const Act& a, const Act* b, Act* out, cudaStream_t st) {
+    const std::string& p = L.prefix;
+    const bool film = cfg.use_scale_shift_norm != 0;
+    const int rmode = L.updown == 2 ? 1 : L.updown == 1 ? 2 : 0;
+    const int Ca = a.C, Cb = b ? b->C : 0;
+    if (Ca + Cb != L.cin) { set_error("plan_res %s: channel mismatch", p.c_str()); return EO_ERR_STATE; }
+    if (rmode == 2 && (a.H % 2 || a.W % 2)) { set_error("down ResBlock %s: odd feature map %dx%d", p.c_str(), a.H, a.W); return EO_ERR_ARG; }
+    if (rmode == 1 && a.H == 3 && a.W == 3) { set_error("up ResBlock: the reference's 3x3 -> 7x7 pad quirk is not implemented"); return EO_ERR_ARG; }
+    const int Ho = rmode == 1 ? a.H * 2 : rmode == 2 ? a.H / 2 : a.H, Wo = rmode == 1 ? a.W * 2 : rmode == 2 ? a.W / 2 : a.W;
+    const bool has_skip = L.cin != L.cout;
+    const int dt = act_dt;
+    int rc;
+    GnOut g1 = plan_gn(p + "in_layers.0", a, b, w(p + "in_layers.0.weight"), w(p + "in_layers.0.bias"));
+    Act hin = new_act(L.cin, Ho, Wo);
+    Act aa = a, bb = b ? *b : Act();
+    const bool two = b != nullptr;
+    const int cin = L.cin;
+    push(p + "in_layers.1.resample", [=](int B, cudaStream_t s) -> int {
+      int r = launch_resample(ptr(aa.off), aa.C, ptr(hin.off), cin, 0, dt, B, aa.H, aa.W, rmode, ptr<float>(g1.scale_off),
+                              ptr<float>(g1.shift_off), g1.C, 0, 1, s);
+      if (r || !two) return r;
+      return launch_resample(ptr(bb.off), bb.C, ptr(hin.off), cin, aa.C, dt, B, bb.H, bb.W, rmode, ptr<float>(g1.scale_off),
+                             ptr<float>(g1.shift_off), g1.C, aa.C, 1, s);
+    }, two ? 2 : 1);
+    note("k_resample", 0, (double)(a.H * a.W + Ho * Wo) * L.cin * dtype_size(act_dt));
+    free_gn(g1);
+    // the skip input: resampled, or concatenated when the block has no skip convolution to read two sources
+    const bool xmat = rmode != 0 || (two && !has_skip);
+    Act xin;
+    if (xmat) {
+      xin = new_act(L.cin, Ho, Wo);
+      push(p + "x_upd", [=](int B, cudaStream_t s) -> int {
+        int r = launch_resample(ptr(aa.off), aa.C, ptr(xin.off), cin, 0, dt, B, aa.H, aa.W, rmode, nullptr, nullptr, 0, 0, 0, s);
+        if (r || !two) return r;
+        return launch_resample(ptr(bb.off), bb.C, ptr(xin.off), cin, aa.C, dt, B, bb.H, bb.W, rmode, nullptr, nullptr, 0, 0, 0, s);
+      }, two ? 2 : 1);
+      note("k_resample", 0, (double)(a.H * a.W + Ho * Wo) * L.cin * dtype_size(act_dt));
+    }
+    const float* w1 = w(p + "in_layers.2.weight");
+    const float* w2 = w(p + "out_layers.3.weight");
+    const float* wsk = has_skip ? w(p + "skip_connection.weight") : nullptr;
+    const float* b1 = film ? w(p + "in_layers.2.bias") : nullptr;     // else folded into the embedding table
+    const int tbo = film ? -1 : L.tb_off;
+    Act h1;
+    if (mode == EO_MODE_FP32) {
+      SrcSpec s0; s0.act = hin;
+      rc = plan_conv_fp32(p + "in_layers.2", {s0}, {{w1, L.cin, 3, 0, L.cin}}, L.cout, b1, nullptr, tbo, nullptr, 1, 0, &h1, st);
+    } else {
+      rc = plan_conv_tc(p + "in_layers.2", {seg3x3(hin)}, {{w1, L.cin, 3, 0, L.cin}}, L.cout, nullptr, b1, nullptr, tbo, nullptr,
+                        Ho, Wo, &h1, st);
+    }
+    if (rc) return rc;
+    free_act(hin);
+    GnOut g2 = plan_gn(p + "out_layers.0", h1, nullptr, w(p + "out_layers.0.weight"), w(p + "out_layers.0.bias"));
+    if (film) {
+      const int toff = L.tb_off, cout = L.cout;
+      push(p + "out_layers.0.film", [=](int B, cudaStream_t s) -> int {
+        return launch_gn_modulate(ptr<float>(g2.scale_off), ptr<float>(g2.shift_off), tb, tb_total, toff, B, cout, s);
+      });
+      note("k_gn_modulate", 0, 0);
+    }
+    const float* b2 = w(p + "out_layers.3.bias");
+    const float* bsk = has_skip ? w(p + "skip_connection.bias") : nullptr;
+    const Act* resid = has_skip ? nullptr : (xmat ? &xin : &a);
+    if (mode == EO_MODE_FP32) {
+      std::vector<SrcSpec> s2; std::vector<PackSeg> sg2;
+      SrcSpec t0; t0.act = h1; t0.gn = &g2; t0.silu = 1; s2.push_back(t0);
+      sg2.push_back({w2, L.cout, 3, 0, L.cout});
+      if (has_skip) {
+        if (xmat) { SrcSpec t1; t1.act = xin; t1.ksize = 1; s2.push_back(t1); sg2.push_back({wsk, L.cin, 1, 0, L.cin}); }
+        else {
+          SrcSpec t1; t1.act = a; t1.ksize = 1; s2.push_back(t1); sg2.push_back({wsk, L.cin, 1, 0, Ca});
+          if (b) { SrcSpec t2; t2.act = *b; t2.ksize = 1; s2.push_back(t2); sg2.push_back({wsk, L.cin, 1, Ca, Cb}); }
+        }
+      }
+      rc = plan_conv_fp32(p + "out_layers.3", s2, sg2, L.cout, b2, bsk, -1, resid, 1, 0, out, st);
+      if (rc) return rc;
+      free_gn(g2);
+      free_act(h1);
+    } else {
+      const bool fuse2 = can_fuse_gn(3, Ho, Wo, L.cout);
+      Act hn;
+      std::vector<TcSegSpec> ts; std::vector<PackSeg> sg;
+      if (fuse2) ts.push_back(with_gn(seg3x3(h1), g2, 0, 1));
+      else { hn = plan_gn_apply(p + "out_layers.0", h1, nullptr, g2, 1); free_gn(g2); free_act(h1); ts.push_back(seg3x3(hn)); }
+      sg.push_back({w2, L.cout, 3, 0, L.cout});
+      if (has_skip) {
+        if (xmat) { ts.push_back(seg1x1(xin)); sg.push_back({wsk, L.cin, 1, 0, L.cin}); }
+        else {
+          ts.push_back(seg1x1(a)); sg.push_back({wsk, L.cin, 1, 0, Ca});
+          if (b) { ts.push_back(seg1x1(*b)); sg.push_back({wsk, L.cin, 1, Ca, Cb}); }
+        }
+      }
+      rc = plan_conv_tc(p + "out_layers.3", ts, sg, L.cout, nullptr, b2, bsk, -1, resid, Ho, Wo, out, st);
+      if (rc) return rc;
+      if (fuse2) { free_gn(g2); free_act(h1); } else free_act(hn);
+    }
+    if (xmat) free_act(xin);
+    return EO_OK;
+  }
+
   // ResBlock._forward (unet_openai.py:365-385); x = cat(a, b) when b != nullptr (:773)
   int plan_res(const Layer& L, const Act& a, const Act* b, Act* out, cudaStream_t st) {
+    if (cfg.use_scale_shift_norm || L.updown) return plan_res_x(L, a, b, out, st);
     const std::string& p = L.prefix;
     const int Ca = a.C, Cb = b ? b->C : 0;
     if (Ca + Cb != L.cin) { set_error("plan_res %s: channel mismatch", p.c_str()); return EO_ERR_STATE; }
@@ -900,11 +1010,14 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
   auto cat_emb = [&](const Block& blk) -> int {
     for (const Layer& L : blk.layers) {
       if (L.kind != L_RES) continue;
+      const bool film = cfg.use_scale_shift_norm != 0;
+      const int erows = (film ? 2 : 1) * L.cout;
       EO_CHECK_CUDA(cudaMemcpyAsync(w_emb_cat + (size_t)L.tb_off * ted, w(L.prefix + "emb_layers.1.weight"),
-                                    (size_t)L.cout * ted * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      // emb bias + the bias of the conv that the embedding is added to (in_layers.2)
-      int r = launch_pack_bias(w(L.prefix + "emb_layers.1.bias"), w(L.prefix + "in_layers.2.bias"),
-                               b_emb_cat + L.tb_off, L.cout, nullptr, st);
+                                    (size_t)erows * ted * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      // emb bias + the bias of the conv that the embedding is added to (in_layers.2); with FiLM the row is
+      // (scale | shift) and the conv keeps its own bias
+      int r = launch_pack_bias(w(L.prefix + "emb_layers.1.bias"), film ? nullptr : w(L.prefix + "in_layers.2.bias"),
+                               b_emb_cat + L.tb_off, erows, nullptr, st);
       if (r) return r;
     }
     return EO_OK;
@@ -1258,8 +1371,6 @@ int eo_unet_create(const eo_unet_cfg* cfg, eo_unet** out) {
   EO_REQUIRE(cfg && out, EO_ERR_ARG, "eo_unet_create: null argument");
   EO_REQUIRE(cfg->dims == 2, EO_ERR_ARG, "eo_unet_create: only dims=2 is implemented (got %d)", cfg->dims);
   EO_REQUIRE(cfg->conv_resample == 1, EO_ERR_ARG, "eo_unet_create: conv_resample=False is not implemented");
-  EO_REQUIRE(cfg->use_scale_shift_norm == 0, EO_ERR_ARG, "eo_unet_create: use_scale_shift_norm=True is not implemented");
-  EO_REQUIRE(cfg->resblock_updown == 0, EO_ERR_ARG, "eo_unet_create: resblock_updown=True is not implemented");
   EO_REQUIRE(cfg->n_channel_mult >= 1 && cfg->n_channel_mult <= 8, EO_ERR_ARG, "eo_unet_create: channel_mult length");
   EO_REQUIRE(cfg->n_attention_resolutions >= 0 && cfg->n_attention_resolutions <= 8, EO_ERR_ARG,
              "eo_unet_create: attention_resolutions length");

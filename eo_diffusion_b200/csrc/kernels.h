@@ -108,6 +108,12 @@ int launch_upsample2x(const void* src, void* dst, int B, int H, int W, int C, cu
 // dst[(hp*2+wp)][b][h2][w2][c] = src[b][2*h2+hp][2*w2+wp][c]; planes are Bstride images apart
 int launch_space_to_depth(const void* src, void* dst, int B, int Bstride, int H, int W, int C,
                           cudaStream_t st);
+// dst[b, ho, wo, coff + c] = resample(act(src * scale[b, gc + c] + shift[b, gc + c])): mode 0 same grid, 1 nearest x2,
+// 2 average of 2x2; scale/shift may be null; src/dst NHWC of dtype dt (up/down ResBlocks, unet_openai.py:366-371)
+int launch_resample(const void* src, int Cs, void* dst, int Cd, int coff, int dt, int B, int Hi, int Wi, int mode,
+                    const float* scale, const float* shift, int gld, int gc, int silu, cudaStream_t st);
+// FiLM on a folded GroupNorm: scale *= 1 + s, shift = shift * (1 + s) + t, (s | t) = tb[b, off .. off + 2C)  (:377-381)
+int launch_gn_modulate(float* scale, float* shift, const float* tb, int ld, int off, int B, int C, cudaStream_t st);
 // tensor-core stem (<= 3 input channels): im2col of cat(x, cond) (NCHW fp32) into 64-channel bf16 NHWC pixels,
 // channels (tap, c) rounded to bf16 then their rounding residuals; and the matching [Cout][64] fp32 weights
 int launch_stem_im2col(const float* x, int Cx, const float* cond, int Cc, void* dst, int B, int H, int W, cudaStream_t st);

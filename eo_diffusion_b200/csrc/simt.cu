@@ -961,6 +961,121 @@ int launch_nhwc_to_nchw_f32(const void* src, int dt, float* dst, int B, int HW, 
 }
 
 // =======================================================================================
+// ResBlock variants of the reference's UNet / UNetBig / UNetSmall factories (unet_openai.py:783-922):
+// up/down-sampling blocks (:321-328, :366-371) and scale-shift (FiLM) conditioning (:377-381)
+// =======================================================================================
+namespace {
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float v[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(p); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float v[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  static __device__ __forceinline__ float act(float x) { return silu_acc(x); }
+};
+template <> struct VecIO<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float v[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(w[e] << 16); v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float v[8]) {
+    uint4 q;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>(p) = q;
+  }
+  static __device__ __forceinline__ float act(float x) { return silu_f(x); }
+};
+
+// dst[b, ho, wo, coff + c] = resample(act(src[b, hi, wi, c] * scale[b, gc + c] + shift[b, gc + c]))
+//   mode 0: identity grid; 1: nearest x2 (F.interpolate, Upsample without conv); 2: 2x2 average (AvgPool2d,
+//   Downsample without conv), taken AFTER the affine + activation like the reference (h_upd follows SiLU)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_resample(const T* __restrict__ src, int Cs, T* __restrict__ dst, int Cd, int coff, int Hi, int Wi, int Ho, int Wo, int mode,
+           const float* __restrict__ scale, const float* __restrict__ shift, int gld, int gc, int silu, long long total) {
+  constexpr int N = VecIO<T>::N;
+  const int cv = Cs / N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * N;
+    long long r = i / cv;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const long long b = r / Ho;
+    float sc[N], sh[N];
+    if (scale) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) { sc[j] = scale[b * gld + gc + c + j]; sh[j] = shift[b * gld + gc + c + j]; }
+    }
+    auto fetch = [&](int hi, int wi, float v[N]) {
+      VecIO<T>::load(src + ((b * Hi + hi) * Wi + wi) * Cs + c, v);
+      if (scale) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+      }
+      if (silu) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = VecIO<T>::act(v[j]);
+      }
+    };
+    float o[N];
+    if (mode == 2) {
+      float v0[N], v1[N], v2[N], v3[N];
+      fetch(2 * ho, 2 * wo, v0); fetch(2 * ho, 2 * wo + 1, v1); fetch(2 * ho + 1, 2 * wo, v2); fetch(2 * ho + 1, 2 * wo + 1, v3);
+#pragma unroll
+      for (int j = 0; j < N; ++j) o[j] = ((v0[j] + v1[j]) + (v2[j] + v3[j])) * 0.25f;
+    } else {
+      fetch(mode == 1 ? ho >> 1 : ho, mode == 1 ? wo >> 1 : wo, o);
+    }
+    VecIO<T>::store(dst + ((b * Ho + ho) * Wo + wo) * Cd + coff + c, o);
+  }
+}
+
+// GroupNorm folded to x * scale + shift, then FiLM: (x * scale + shift) * (1 + s) + t with (s | t) = the block's
+// row of the per-step embedding table -> scale *= (1 + s); shift = shift * (1 + s) + t        (unet_openai.py:378-380)
+__global__ void k_gn_modulate(float* __restrict__ scale, float* __restrict__ shift, const float* __restrict__ tb, int ld, int off,
+                              int B, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const float s1 = 1.0f + tb[(long long)b * ld + off + c], t = tb[(long long)b * ld + off + C + c];
+  const float sc = scale[i], sh = shift[i];
+  scale[i] = sc * s1;
+  shift[i] = fmaf(sh, s1, t);
+}
+}  // namespace
+
+int launch_resample(const void* src, int Cs, void* dst, int Cd, int coff, int dt, int B, int Hi, int Wi, int mode,
+                    const float* scale, const float* shift, int gld, int gc, int silu, cudaStream_t st) {
+  const int N = dt == DT_F32 ? 4 : 8;
+  EO_REQUIRE(Cs % N == 0 && Cd % N == 0 && coff % N == 0, EO_ERR_ARG, "resample: channel counts must be multiples of %d", N);
+  EO_REQUIRE(mode != 2 || (Hi % 2 == 0 && Wi % 2 == 0), EO_ERR_ARG, "resample: odd feature map %dx%d", Hi, Wi);
+  const int Ho = mode == 1 ? 2 * Hi : mode == 2 ? Hi / 2 : Hi, Wo = mode == 1 ? 2 * Wi : mode == 2 ? Wi / 2 : Wi;
+  const long long total = (long long)B * Ho * Wo * (Cs / N);
+  if (dt == DT_F32)
+    k_resample<float><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float*>(src), Cs, reinterpret_cast<float*>(dst), Cd, coff,
+                                                       Hi, Wi, Ho, Wo, mode, scale, shift, gld, gc, silu, total);
+  else
+    k_resample<__nv_bfloat16><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), Cs,
+                                                               reinterpret_cast<__nv_bfloat16*>(dst), Cd, coff, Hi, Wi, Ho, Wo, mode,
+                                                               scale, shift, gld, gc, silu, total);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+int launch_gn_modulate(float* scale, float* shift, const float* tb, int ld, int off, int B, int C, cudaStream_t st) {
+  k_gn_modulate<<<ceil_div((long long)B * C, 256), 256, 0, st>>>(scale, shift, tb, ld, off, B, C);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+
+// =======================================================================================
 // tensor-core stem and head (bf16 mode): layout passes either side of k_conv_tc
 // =======================================================================================
 namespace {

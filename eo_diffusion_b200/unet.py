@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from . import _lib
 
-__all__ = ["UNetModel", "ResBlock", "AttentionBlock", "Downsample", "Upsample",
+__all__ = ["UNetModel", "UNet", "UNetBig", "UNetSmall", "ResBlock", "AttentionBlock", "Downsample", "Upsample",
            "TimestepEmbedSequential", "GroupNorm32", "timestep_embedding"]
 
 
@@ -69,19 +69,40 @@ class TimestepEmbedSequential(nn.Sequential):
         return _EngineBlock.forward(self)
 
 
-class ResBlock(_EngineBlock):
-    """Parameters of reference ResBlock (:274-385), non-updown, additive embedding."""
+class _Resample(nn.Module):
+    """Parameter-free Upsample(use_conv=False) / Downsample(use_conv=False) holder (reference :211-271):
+    keeps the `h_upd` / `x_upd` module names of an up/down ResBlock."""
 
-    def __init__(self, channels, emb_channels, dropout, out_channels=None):
+    def __init__(self, channels, up):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = channels
+        self.use_conv = False
+        self.up = up
+
+
+class ResBlock(_EngineBlock):
+    """Parameters of reference ResBlock (:274-385): additive or scale-shift (FiLM) embedding, optionally an
+    up- or down-sampling block (`resblock_updown`)."""
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_scale_shift_norm=False,
+                 up=False, down=False):
         super().__init__()
         self.channels = channels
         self.emb_channels = emb_channels
         self.dropout = dropout
         self.out_channels = out_channels or channels
+        self.use_scale_shift_norm = use_scale_shift_norm
+        self.updown = up or down
         oc = self.out_channels
         self.in_layers = nn.Sequential(GroupNorm32(32, channels), nn.SiLU(),
                                        nn.Conv2d(channels, oc, 3, padding=1))
-        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, oc))
+        if up or down:
+            self.h_upd = _Resample(channels, up)
+            self.x_upd = _Resample(channels, up)
+        else:
+            self.h_upd = self.x_upd = nn.Identity()
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, 2 * oc if use_scale_shift_norm else oc))
         self.out_layers = nn.Sequential(GroupNorm32(32, oc), nn.SiLU(), nn.Dropout(p=dropout),
                                         _zeroed(nn.Conv2d(oc, oc, 3, padding=1)))
         self.skip_connection = nn.Identity() if oc == channels else nn.Conv2d(channels, oc, 1)
@@ -137,9 +158,8 @@ def _destroy_handle(handle):
 
 
 class UNetModel(nn.Module):
-    """Same constructor as the reference (:553-575).  Options the sampling path of the
-    reference never exercises (`dims != 2`, `conv_resample=False`, `use_scale_shift_norm`,
-    `resblock_updown`) raise NotImplementedError here rather than silently diverging.
+    """Same constructor as the reference (:553-575).  `dims != 2` and `conv_resample=False`, which no
+    configuration of the reference sets, raise NotImplementedError rather than silently diverging.
 
     Additive API: `compute_mode` ("bf16": tcgen05 tensor-core kernels, the default, or
     "fp32": fp32 CUDA-core kernels for parity checks), selectable with `set_compute_mode`
@@ -152,10 +172,10 @@ class UNetModel(nn.Module):
                  use_scale_shift_norm=False, resblock_updown=False,
                  use_new_attention_order=False):
         super().__init__()
-        if dims != 2 or not conv_resample or use_scale_shift_norm or resblock_updown:
+        if dims != 2 or not conv_resample:
             raise NotImplementedError(
-                "eo_diffusion_b200.UNetModel implements the reference's sampling configuration "
-                "(dims=2, conv_resample=True, use_scale_shift_norm=False, resblock_updown=False)")
+                "eo_diffusion_b200.UNetModel implements the reference's 2-D configurations "
+                "(dims=2, conv_resample=True)")
         if num_heads_upsample == -1:
             num_heads_upsample = num_heads
         self.image_size = image_size
@@ -175,6 +195,9 @@ class UNetModel(nn.Module):
         self.num_head_channels = num_head_channels
         self.num_heads_upsample = num_heads_upsample
         self.use_new_attention_order = use_new_attention_order
+        self.use_scale_shift_norm = use_scale_shift_norm
+        self.resblock_updown = resblock_updown
+        ssn = use_scale_shift_norm
 
         ted = model_channels * time_emb_factor
         self.time_embed = nn.Sequential(nn.Linear(model_channels, ted), nn.SiLU(), nn.Linear(ted, ted))
@@ -193,7 +216,7 @@ class UNetModel(nn.Module):
         ds = 1
         for level, mult in enumerate(channel_mult):
             for _ in range(num_res_blocks):
-                layers = [ResBlock(ch, ted, dropout, out_channels=int(mult * model_channels))]
+                layers = [ResBlock(ch, ted, dropout, out_channels=int(mult * model_channels), use_scale_shift_norm=ssn)]
                 ch = int(mult * model_channels)
                 if ds in attention_resolutions:
                     layers.append(attn(ch, num_heads))
@@ -201,25 +224,29 @@ class UNetModel(nn.Module):
                 self._feature_size += ch
                 skip_chans.append(ch)
             if level != len(channel_mult) - 1:
-                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, out_channels=ch)))
+                self.input_blocks.append(TimestepEmbedSequential(
+                    ResBlock(ch, ted, dropout, out_channels=ch, use_scale_shift_norm=ssn, down=True)
+                    if resblock_updown else Downsample(ch, out_channels=ch)))
                 skip_chans.append(ch)
                 ds *= 2
                 self._feature_size += ch
 
         self.middle_block = TimestepEmbedSequential(
-            ResBlock(ch, ted, dropout), attn(ch, num_heads), ResBlock(ch, ted, dropout))
+            ResBlock(ch, ted, dropout, use_scale_shift_norm=ssn), attn(ch, num_heads),
+            ResBlock(ch, ted, dropout, use_scale_shift_norm=ssn))
         self._feature_size += ch
 
         self.output_blocks = nn.ModuleList([])
         for level, mult in list(enumerate(channel_mult))[::-1]:
             for i in range(num_res_blocks + 1):
                 ich = skip_chans.pop()
-                layers = [ResBlock(ch + ich, ted, dropout, out_channels=int(model_channels * mult))]
+                layers = [ResBlock(ch + ich, ted, dropout, out_channels=int(model_channels * mult), use_scale_shift_norm=ssn)]
                 ch = int(model_channels * mult)
                 if ds in attention_resolutions:
                     layers.append(attn(ch, num_heads_upsample))
                 if level and i == num_res_blocks:
-                    layers.append(Upsample(ch, out_channels=ch))
+                    layers.append(ResBlock(ch, ted, dropout, out_channels=ch, use_scale_shift_norm=ssn, up=True)
+                                  if resblock_updown else Upsample(ch, out_channels=ch))
                     ds //= 2
                 self.output_blocks.append(TimestepEmbedSequential(*layers))
                 self._feature_size += ch
@@ -275,7 +302,9 @@ class UNetModel(nn.Module):
         c.num_head_channels = self.num_head_channels
         c.num_heads_upsample = self.num_heads_upsample
         c.use_new_attention_order = int(bool(self.use_new_attention_order))
-        c.dims, c.conv_resample, c.use_scale_shift_norm, c.resblock_updown = 2, 1, 0, 0
+        c.dims, c.conv_resample = 2, 1
+        c.use_scale_shift_norm = int(bool(self.use_scale_shift_norm))
+        c.resblock_updown = int(bool(self.resblock_updown))
         return c
 
     def _ensure_handle(self):
@@ -368,3 +397,35 @@ class UNetModel(nn.Module):
                                          _lib.ptr(ts), _lib.ptr(yy), _lib.ptr(out), B, _lib.stream_ptr()),
                        "eo_unet_forward")
         return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+
+def _factory(image_size, in_channels, out_channels, base_width, num_classes, num_res_blocks, mults, head_channels=64,
+             time_emb_factor=4):
+    # the reference's UNetBig / UNet / UNetSmall (unet_openai.py:783-922): same tables, same flags
+    if image_size not in mults:
+        raise ValueError(f"unsupported image size: {image_size}")
+    attention_resolutions = "28,14,7" if image_size == 28 else "32,16,8"
+    attention_ds = tuple(image_size // int(res) for res in attention_resolutions.split(","))
+    return UNetModel(image_size=image_size, in_channels=in_channels, model_channels=base_width,
+                     out_channels=out_channels, num_res_blocks=num_res_blocks, attention_resolutions=attention_ds,
+                     time_emb_factor=time_emb_factor, dropout=0.1, channel_mult=mults[image_size], num_classes=num_classes, use_checkpoint=False,
+                     use_fp16=False, num_heads=4, num_head_channels=head_channels, num_heads_upsample=-1,
+                     use_scale_shift_norm=True, resblock_updown=True, use_new_attention_order=True)
+
+_MULTS = {128: (1, 1, 2, 3, 4), 64: (1, 2, 3, 4), 32: (1, 2, 2, 2), 28: (1, 2, 2, 2)}
+
+
+def UNetBig(image_size, in_channels=3, out_channels=3, base_width=192, num_classes=None):
+    """Reference factory (unet_openai.py:783-828): 3 res blocks per level."""
+    return _factory(image_size, in_channels, out_channels, base_width, num_classes, 3, _MULTS)
+
+
+def UNet(image_size, in_channels=3, out_channels=3, base_width=64, num_classes=None):
+    """Reference factory (unet_openai.py:830-875)."""
+    return _factory(image_size, in_channels, out_channels, base_width, num_classes, 3, _MULTS)
+
+
+def UNetSmall(image_size, in_channels=3, out_channels=3, base_width=32, num_classes=None):
+    """Reference factory (unet_openai.py:877-922): 2 res blocks per level, 32-channel heads, time_emb_factor 2."""
+    return _factory(image_size, in_channels, out_channels, base_width, num_classes, 2, _MULTS, head_channels=32,
+                    time_emb_factor=2)

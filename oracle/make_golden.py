@@ -127,7 +127,12 @@ def hook_eps(diff, rec):
 manifest = {"reference": "furio1999/EO_Diffusion", "torch": torch.__version__, "cases": {}}
 
 
+ONLY = os.environ.get("EO_GOLDEN_ONLY", "")   # substring filter: regenerate matching cases only (manifest merged)
+
+
 def save(name, pinned, **arrs):
+    if ONLY and ONLY not in name:
+        return
     out = {}
     for k, v in arrs.items():
         if isinstance(v, torch.Tensor):
@@ -240,6 +245,21 @@ def main():
     eps_case("tiny_concat_eps", dict(TINY, in_channels=5), 2, [250, 3], cond_ch=2)
     eps_case("small_eps", SMALL, 2, [999, 1])
     eps_case("small_ms_concat_eps", dict(SMALL, in_channels=28, out_channels=13), 1, [400], cond_ch=15)
+    # the switches of the reference's UNet / UNetBig / UNetSmall factories (unet_openai.py:783-922)
+    eps_case("tiny_film_eps", dict(TINY, use_scale_shift_norm=True), 2, [999, 3])
+    eps_case("tiny_updown_eps", dict(TINY, resblock_updown=True), 2, [700, 0])
+    eps_case("tiny_film_updown_eps", dict(TINY, use_scale_shift_norm=True, resblock_updown=True), 2, [250, 9])
+    eps_case("small_film_updown_eps", dict(SMALL, use_scale_shift_norm=True, resblock_updown=True, num_head_channels=32,
+                                           use_new_attention_order=True), 2, [999, 1])
+    if ONLY:
+        path = os.path.join(GOLD, "MANIFEST.json")
+        with open(path) as f:
+            old = json.load(f)
+        old["cases"].update(manifest["cases"])
+        with open(path, "w") as f:
+            json.dump(old, f, indent=1, sort_keys=True)
+        print("done (only:", ONLY + ")")
+        return
     m_base, sd_base = eps_case("base64_eps", BASE, 1, [999])
     nparam = sum(p.numel() for p in m_base.parameters())
     assert nparam == 88220934, nparam  # EO_Diffusion.ipynb:151

@@ -55,12 +55,12 @@ def full_cfg(**kw) -> dict:
 def enumerate_blocks(cfg: dict) -> Dict[str, list]:
     """Walk the constructor loops of UNetModel (unet_openai.py:607-737) and return, per
     stage, the list of sub-layers as tuples:
-      ("conv_in", cin, cout) | ("res", cin, cout) | ("attn", ch, heads) |
+      ("conv_in", cin, cout) | ("res", cin, cout[, "down" | "up"]) | ("attn", ch, heads) |
       ("down", ch) | ("up", ch)
-    Only the options the hot path exercises are restated (dims=2, conv_resample=True,
-    resblock_updown=False, use_scale_shift_norm=False)."""
-    assert cfg["dims"] == 2 and cfg["conv_resample"] and not cfg["resblock_updown"]
-    assert not cfg["use_scale_shift_norm"]
+    With resblock_updown the Downsample / Upsample slots hold a ResBlock(down=True / up=True) instead
+    (:645-658, :722-735).  dims=2 and conv_resample=True only."""
+    assert cfg["dims"] == 2 and cfg["conv_resample"]
+    rud = bool(cfg["resblock_updown"])
     mc = cfg["model_channels"]
     mult = list(cfg["channel_mult"])
     nrb = cfg["num_res_blocks"]
@@ -85,7 +85,7 @@ def enumerate_blocks(cfg: dict) -> Dict[str, list]:
             inputs.append(layers)
             chans.append(ch)
         if level != len(mult) - 1:
-            inputs.append([("down", ch)])
+            inputs.append([("res", ch, ch, "down")] if rud else [("down", ch)])
             chans.append(ch)
             ds *= 2
     middle = [("res", ch, ch), ("attn", ch, nheads(ch, heads)), ("res", ch, ch)]
@@ -98,7 +98,7 @@ def enumerate_blocks(cfg: dict) -> Dict[str, list]:
             if ds in attn_res:
                 layers.append(("attn", ch, nheads(ch, heads_up)))
             if level and i == nrb:
-                layers.append(("up", ch))
+                layers.append(("res", ch, ch, "up") if rud else ("up", ch))
                 ds //= 2
             outputs.append(layers)
     return {"input": inputs, "middle": middle, "output": outputs, "final_ch": ch}
@@ -126,14 +126,30 @@ def group_norm32(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
     return F.group_norm(x.float(), 32, w, b, 1e-5).type(x.dtype)
 
 
-def res_block(sd: dict, p: str, x: Tensor, emb: Tensor) -> Tensor:
-    """ResBlock._forward, non-updown, no scale-shift (unet_openai.py:365-385)."""
+def res_block(sd: dict, p: str, x: Tensor, emb: Tensor, updown: Optional[str] = None,
+              scale_shift: bool = False) -> Tensor:
+    """ResBlock._forward (unet_openai.py:365-385).  `updown` "up" / "down": h_upd / x_upd are
+    Upsample / Downsample WITHOUT convolution (:321-328 -> nearest x2, :229-242 / AvgPool2d(2), :263-266),
+    applied between SiLU and the first convolution and to the skip input (:366-371).  `scale_shift`:
+    FiLM conditioning `out_norm(h) * (1 + scale) + shift` (:377-381)."""
     h = group_norm32(x, sd[p + "in_layers.0.weight"], sd[p + "in_layers.0.bias"])
     h = F.silu(h)
+    if updown == "up":
+        assert not (x.shape[-1] == x.shape[-2] == 3)
+        h = F.interpolate(h, scale_factor=2, mode="nearest")
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    elif updown == "down":
+        h = F.avg_pool2d(h, kernel_size=2, stride=2)
+        x = F.avg_pool2d(x, kernel_size=2, stride=2)
     h = F.conv2d(h, sd[p + "in_layers.2.weight"], sd[p + "in_layers.2.bias"], padding=1)
     e = F.linear(F.silu(emb), sd[p + "emb_layers.1.weight"], sd[p + "emb_layers.1.bias"])
-    h = h + e.type(h.dtype)[..., None, None]
-    h = group_norm32(h, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"])
+    e = e.type(h.dtype)[..., None, None]
+    if scale_shift:
+        scale, shift = torch.chunk(e, 2, dim=1)
+        h = group_norm32(h, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"]) * (1 + scale) + shift
+    else:
+        h = h + e
+        h = group_norm32(h, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"])
     h = F.silu(h)
     # Dropout(p=dropout) at out_layers.2: identity at inference / p=0
     h = F.conv2d(h, sd[p + "out_layers.3.weight"], sd[p + "out_layers.3.bias"], padding=1)
@@ -189,14 +205,14 @@ def upsample(sd: dict, p: str, x: Tensor) -> Tensor:
     return F.conv2d(out, sd[p + "conv.weight"], sd[p + "conv.bias"], padding=1)
 
 
-def _run_layers(sd, prefix, layers, h, emb, new_order):
+def _run_layers(sd, prefix, layers, h, emb, new_order, scale_shift=False):
     for j, layer in enumerate(layers):
         p = f"{prefix}{j}."
         kind = layer[0]
         if kind == "conv_in":
             h = F.conv2d(h, sd[p + "weight"], sd[p + "bias"], padding=1)
         elif kind == "res":
-            h = res_block(sd, p, h, emb)
+            h = res_block(sd, p, h, emb, layer[3] if len(layer) > 3 else None, scale_shift)
         elif kind == "attn":
             h = attention_block(sd, p, h, layer[2], new_order)
         elif kind == "down":
@@ -220,6 +236,7 @@ def unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, timesteps: Tensor,
         "must specify y if and only if the model is class-conditional"
     blocks = enumerate_blocks(cfg)
     new_order = cfg["use_new_attention_order"]
+    ssn = bool(cfg["use_scale_shift_norm"])
     emb = timestep_embedding(timesteps, cfg["model_channels"])
     emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
@@ -229,16 +246,16 @@ def unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, timesteps: Tensor,
     hs = []
     h = x.float()
     for i, layers in enumerate(blocks["input"]):
-        h = _run_layers(sd, f"input_blocks.{i}.", layers, h, emb, new_order)
+        h = _run_layers(sd, f"input_blocks.{i}.", layers, h, emb, new_order, ssn)
         hs.append(h)
         if taps is not None:
             taps[f"input_blocks.{i}"] = h
-    h = _run_layers(sd, "middle_block.", blocks["middle"], h, emb, new_order)
+    h = _run_layers(sd, "middle_block.", blocks["middle"], h, emb, new_order, ssn)
     if taps is not None:
         taps["middle_block"] = h
     for i, layers in enumerate(blocks["output"]):
         h = torch.cat([h, hs.pop()], dim=1)
-        h = _run_layers(sd, f"output_blocks.{i}.", layers, h, emb, new_order)
+        h = _run_layers(sd, f"output_blocks.{i}.", layers, h, emb, new_order, ssn)
         if taps is not None:
             taps[f"output_blocks.{i}"] = h
     h = h.type(x.dtype)

@@ -39,7 +39,9 @@ def model_for(g, dev, mode):
 
 @pytest.mark.parametrize("name", ["tiny_eps", "tiny_eps_b3", "tiny_concat_eps", "small_eps",
                                   "small_ms_concat_eps", "base64_eps", "base64_eps_t500",
-                                  "base64_eps_t1", "base64_eps_t0"])
+                                  "base64_eps_t1", "base64_eps_t0",
+                                  # FiLM conditioning / up-down ResBlocks (the reference's UNet* factories)
+                                  "tiny_film_eps", "tiny_updown_eps", "tiny_film_updown_eps", "small_film_updown_eps"])
 def test_eps_fp32_mode(cuda_dev, name):
     g = golden(name)
     m, _ = model_for(g, cuda_dev, "fp32")
@@ -52,7 +54,7 @@ def test_eps_fp32_mode(cuda_dev, name):
 
 
 @pytest.mark.parametrize("name", ["small_eps", "small_ms_concat_eps", "base64_eps", "base64_eps_t500",
-                                  "base64_eps_t1", "base64_eps_t0"])
+                                  "base64_eps_t1", "base64_eps_t0", "small_film_updown_eps"])
 def test_eps_bf16_mode(cuda_dev, name):
     g = golden(name)
     m, _ = model_for(g, cuda_dev, "bf16")

@@ -49,15 +49,15 @@ def test_product_does_not_import_oracle():
 
 
 def test_unsupported_ctor_options_raise():
-    for kw in (dict(dims=3), dict(conv_resample=False), dict(use_scale_shift_norm=True),
-               dict(resblock_updown=True)):
+    for kw in (dict(dims=3), dict(conv_resample=False)):
         with pytest.raises(NotImplementedError):
             UNetModel(**dict(TINY, **kw))
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
 @pytest.mark.parametrize("extra", [{}, dict(in_channels=5, num_classes=7, num_head_channels=16,
-                                            use_new_attention_order=True)])
+                                            use_new_attention_order=True),
+                                   dict(use_scale_shift_norm=True, resblock_updown=True)])
 def test_state_dict_identical_to_reference(extra):
     sys.path.insert(0, REFERENCE)
     try:
@@ -125,3 +125,24 @@ def test_ddim_broken_reference_branches_refuse():
     smp = DDIMSampler(d)
     with pytest.raises(NotImplementedError):
         smp.sample(4, 1, (3, 8, 8), mask=torch.ones(1, 1, 8, 8), x0=torch.zeros(1, 3, 8, 8), verbose=False)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+@pytest.mark.parametrize("factory,size", [("UNet", 32), ("UNetSmall", 64), ("UNetBig", 28)])
+def test_factories_identical_to_reference(factory, size):
+    """UNet / UNetBig / UNetSmall (unet_openai.py:783-922): same tables, flags and initial weights."""
+    sys.path.insert(0, REFERENCE)
+    try:
+        from backbones import unet_openai as R
+    finally:
+        sys.path.remove(REFERENCE)
+    from eo_diffusion_b200 import unet as U
+    torch.manual_seed(7)
+    a = getattr(R, factory)(size, num_classes=5)
+    torch.manual_seed(7)
+    b = getattr(U, factory)(size, num_classes=5)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    with pytest.raises(ValueError, match="unsupported image size"):
+        getattr(U, factory)(48)
