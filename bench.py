@@ -308,11 +308,22 @@ def run_ours(args, wl):
     launches_step = model.launches_per_forward() + 1
 
     # ---- end to end through the public API from pinned host buffers ---------------------------
+    # Every step copies ITS inputs host -> device and its result device -> host inside the timed region.  The copies run
+    # on a side stream into double-buffered device tensors, so step k+1's inputs travel while step k computes (a
+    # sampler's noise / conditioning for the next step do not depend on the current one); the result goes back on a
+    # third stream.  The first step's inputs and the last step's result are not overlapped with anything.
     hx = host["x"].clone().pin_memory()
     out_host = torch.empty_like(hx).pin_memory()
-    dx, dn, dgt, dm = (torch.empty_like(d["x"]), torch.empty_like(d["x"]), torch.empty_like(d["gt"]),
-                       torch.empty_like(d["mask"]))
-    dcond = torch.empty_like(d["cond"]) if kind == "concat" else None
+
+    def slot_buffers():
+        b = dict(x=torch.empty_like(d["x"]), n=torch.empty_like(d["x"]))
+        if kind == "sum":
+            b["gt"], b["m"] = torch.empty_like(d["gt"]), torch.empty_like(d["mask"])
+        if kind == "concat":
+            b["cond"] = torch.empty_like(d["cond"])
+        return b
+
+    slots = [slot_buffers(), slot_buffers()]
     if kind == "sum":
         h2d = sum(t.numel() * 4 for t in (hx, host["nz0"], host["gt"], host["mask"]))
     elif kind == "concat":
@@ -320,34 +331,65 @@ def run_ours(args, wl):
     else:
         h2d = hx.numel() * 4
     d2h = out_host.numel() * 4
+    main_s = torch.cuda.current_stream()
+    in_s, out_s = torch.cuda.Stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]      # slot's inputs have landed
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]    # the step that read the slot has been enqueued and finished
+    ev_done, ev_out = torch.cuda.Event(), torch.cuda.Event()
 
-    def e2e_step(k):
-        dx.copy_(hx, non_blocking=True)
+    def stage_inputs(k):
+        b = slots[k % 2]
+        in_s.wait_event(ev_free[k % 2])
+        with torch.cuda.stream(in_s):
+            b["x"].copy_(hx, non_blocking=True)
+            if kind != "ddim":
+                b["n"].copy_(host["nz0"] if k % 2 == 0 else host["nz1"], non_blocking=True)
+            if kind == "sum":
+                b["gt"].copy_(host["gt"], non_blocking=True)
+                b["m"].copy_(host["mask"], non_blocking=True)
+            if kind == "concat":
+                b["cond"].copy_(host["cond"], non_blocking=True)
+            ev_in[k % 2].record(in_s)
+
+    def e2e_step(k, last):
+        b = slots[k % 2]
+        if not last:
+            stage_inputs(k + 1)
+        main_s.wait_event(ev_in[k % 2])
+        dx, dn = b["x"], b["n"]
         if kind == "ddim":
             idx = len(ddim_ts) - 1 - (k % len(ddim_ts))
             nxt, _ = sampler.p_sample_ddim(dx, None, ts_rows[ddim_ts[idx]], index=idx)   # public method: UNet + DDIM update
-            out_host.copy_(nxt, non_blocking=True)
-            return
-        i = T_DDPM - 1 - (k % (T_DDPM - 1))
-        dn.copy_(host["nz0"] if k % 2 == 0 else host["nz1"], non_blocking=True)
-        t = ts_rows[i]
-        if kind == "concat":
-            dcond.copy_(host["cond"], non_blocking=True)
-            nxt = diff._reverse_diffusion_with_clip(dx, t, dn, cond=dcond)
         else:
-            dgt.copy_(host["gt"], non_blocking=True)
-            dm.copy_(host["mask"], non_blocking=True)
-            _lib.check(L.eo_ddpm_sum_mix(_lib.ptr(dx), _lib.ptr(dgt), _lib.ptr(dm), _lib.ptr(dn), _lib.ptr(t),
-                                         _lib.ptr(tab), _lib.ptr(dx), B, 3, hw, stream()))
-            nxt = diff._reverse_diffusion_with_clip(dx, t, dn)      # public method: UNet + posterior
-        out_host.copy_(nxt, non_blocking=True)
+            i = T_DDPM - 1 - (k % (T_DDPM - 1))
+            t = ts_rows[i]
+            if kind == "concat":
+                nxt = diff._reverse_diffusion_with_clip(dx, t, dn, cond=b["cond"])
+            else:
+                _lib.check(L.eo_ddpm_sum_mix(_lib.ptr(dx), _lib.ptr(b["gt"]), _lib.ptr(b["m"]), _lib.ptr(dn), _lib.ptr(t),
+                                             _lib.ptr(tab), _lib.ptr(dx), B, 3, hw, stream()))
+                nxt = diff._reverse_diffusion_with_clip(dx, t, dn)      # public method: UNet + posterior
+        ev_free[k % 2].record(main_s)
+        ev_done.record(main_s)
+        main_s.wait_event(ev_out)              # the previous result has left before its buffer can be reused
+        out_s.wait_event(ev_done)
+        with torch.cuda.stream(out_s):
+            out_host.copy_(nxt, non_blocking=True)
+            ev_out.record(out_s)
+        nxt.record_stream(out_s)
 
-    n_e2e = max(2, min(args.steps, 5))
-    e2e_step(0)
+    n_e2e = max(2, args.steps)
+    for ev in ev_free:
+        ev.record(main_s)
+    ev_out.record(out_s)
+    stage_inputs(0)
+    e2e_step(0, True)
     barrier()
     e0.record()
+    stage_inputs(1)
     for k in range(n_e2e):
-        e2e_step(k + 1)
+        e2e_step(k + 1, k == n_e2e - 1)
+    main_s.wait_event(ev_out)                  # the last result is on the host
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1) / n_e2e)

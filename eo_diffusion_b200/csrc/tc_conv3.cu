@@ -78,14 +78,16 @@ struct Smem {
 
 struct Tile { int w0, h0, n0, nbase; };
 
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, const FastDiv& f) { return f.d > 1 ? __umulhi(x, f.mul) >> f.shr : x; }
+
 __device__ __forceinline__ Tile decode_tile(int w, int n_ntiles, uint32_t rank, const Geom3& g, int BN) {
-  const int mp = w / n_ntiles, nt = w - mp * n_ntiles;
-  const int mt = 2 * mp + (int)rank;
+  const uint32_t mp = fast_div((uint32_t)w, g.d_nt), nt = (uint32_t)w - mp * (uint32_t)n_ntiles;
+  const uint32_t mt = 2 * mp + rank;
   Tile t;
-  const int tw = mt % g.tiles_w;
-  const int th = (mt / g.tiles_w) % g.tiles_h;
-  t.w0 = tw * g.bw; t.h0 = th * g.bh; t.n0 = (mt / (g.tiles_w * g.tiles_h)) * g.bn;
-  t.nbase = nt * BN;
+  const uint32_t r1 = fast_div(mt, g.d_tw), tw = mt - r1 * (uint32_t)g.tiles_w;     // mt = (n * tiles_h + th) * tiles_w + tw
+  const uint32_t r2 = fast_div(r1, g.d_th), th = r1 - r2 * (uint32_t)g.tiles_h;
+  t.w0 = (int)tw * g.bw; t.h0 = (int)th * g.bh; t.n0 = (int)r2 * g.bn;
+  t.nbase = (int)nt * BN;
   return t;
 }
 
@@ -104,27 +106,15 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// column sums over the 32 lanes of a warp: on return lane j holds sum_over_lanes(f[j]).
-// Recursive halving: 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
-__device__ __forceinline__ float warp_column_sums(float (&f)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float keep = upper ? f[i + off] : f[i];
-      const float send = upper ? f[i] : f[i + off];
-      f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return f[0];
-}
-
 // development aid (eo_debug_conv_trace, TRACE instantiation only): per-CTA counters, slot = 0 lifetime,
 // 1 MMA waits on operands, 2 MMA waits on a free accumulator, 3 epilogue waits on the accumulator,
 // 4 epilogue busy, 5 producer waits on free stages, 6 tiles, 7 transform warps busy (clock64 ticks)
+// slots 8.. (EO_TRACE_EXT=1, buffer of 2 * n * 8 counters): 8 MMA waits on operand A only, 9 transform warps wait
+// for a free stage
 __device__ __forceinline__ void trace_put(const Epi3& ep, int slot, long long v) {
-  if (ep.trace && (int)blockIdx.x < ep.trace_n) ep.trace[(long long)blockIdx.x * 8 + slot] = v;
+  if (!ep.trace || (int)blockIdx.x >= ep.trace_n) return;
+  if (slot < 8) ep.trace[(long long)blockIdx.x * 8 + slot] = v;
+  else if (ep.hack & 2) ep.trace[((long long)ep.trace_n + blockIdx.x) * 8 + slot - 8] = v;
 }
 #define TRACE_T0() const long long _t0 = TRACE ? clock64() : 0
 #define TRACE_ACC(var) do { if (TRACE) (var) += clock64() - _t0; } while (0)
@@ -211,6 +201,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     // ------------------------------------------------------------------ operand producer
     Ring ra, rb;
     long long tr_wait = 0;
+    uint32_t hk = 0;
     const uint32_t r_full_l = tc::mapa_u32(tc::smem_u32(&r_full[0]), 0);   // the leader's barriers
     const uint32_t b_full_l = tc::mapa_u32(tc::smem_u32(&b_full[0]), 0);
     const int b_row = (int)rank * (BN / 2);
@@ -243,7 +234,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         const int per = en.patch ? TPB : 1;
         for (int j = 0; j < nb; j += per) {
           { TRACE_T0(); tc::mbar_wait(&b_empty[rb.i], rb.ph ^ 1); TRACE_ACC(tr_wait); }
-          if (tc::elect_one()) {
+          const bool skip = (ep.hack & 1) && ((hk++) & 1);
+          if (skip) { if (rank == 0 && tc::elect_one()) tc::mbar_arrive(&b_full[rb.i]); }
+          else if (tc::elect_one()) {
             // one arrival per phase: the leader's producer, which posts the byte count of BOTH CTAs'
             // loads; the peer's TMA only completes transactions on the leader's barrier
             if (rank == 0) tc::mbar_arrive_expect_tx(&b_full[rb.i], 2 * per * b_bytes);
@@ -266,7 +259,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       const uint32_t b_step = (uint32_t)b_stage >> 4, b_tile = (uint32_t)b_bytes >> 4;
       Ring ra, rg, rb;
       uint32_t it = 0;
-      long long tr_ops = 0, tr_acc = 0;
+      long long tr_ops = 0, tr_acc = 0, tr_a = 0;
       for (int w = cid; w < n_work; w += ncl, ++it) {
         const uint32_t ab = it & 1;
         { TRACE_T0(); tc::mbar_wait_cluster(&tmem_empty[ab], ((it >> 1) & 1) ^ 1); TRACE_ACC(tr_acc); }   // both CTAs' epilogues drained this buffer
@@ -280,7 +273,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             TRACE_T0();
             if (gn) tc::mbar_wait_cluster(&g_ready[rg.i], rg.ph);
             else tc::mbar_wait(&r_full[ra.i], ra.ph);
-            TRACE_ACC(tr_ops);
+            TRACE_ACC(tr_ops); TRACE_ACC(tr_a);
           }
           tc::tc_fence_after();
           const uint32_t a_base = tc::smem_u32(gn ? smem_g + rg.i * A_STAGE : smem_a + ra.i * A_STAGE);
@@ -327,7 +320,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           if (gn) rg.next((uint32_t)SAG); else ra.next((uint32_t)SAR);
         }
       }
-      if (TRACE && lane == 0) { trace_put(ep, 1, tr_ops); trace_put(ep, 2, tr_acc); trace_put(ep, 6, it); }
+      if (TRACE && lane == 0) { trace_put(ep, 1, tr_ops); trace_put(ep, 2, tr_acc); trace_put(ep, 6, it); trace_put(ep, 8, tr_a); }
     }
   } else if (warp == 2 || warp == 3) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -367,7 +360,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     // left, right; bit 20 = beyond the patch); plin = pixel offset inside the image relative to the
     // patch origin
     uint32_t ptab[XF_PIX];
-    int plin[XF_PIX];
+    uint32_t plin[XF_PIX];
 #pragma unroll
     for (int i = 0; i < XF_PIX; ++i) {
       const int q = pl + 4 * XF_WARPS * i;
@@ -375,7 +368,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       uint32_t edge = (ph == 0 ? 1u : 0u) | (ph == PATCH_H - 1 ? 2u : 0u) | (pw == 0 ? 4u : 0u) | (pw == PATCH_W - 1 ? 8u : 0u);
       if (q >= PATCH_W * PATCH_H) edge = 16u;
       ptab[i] = (uint32_t)(q * 128 + ((ch8 ^ (q & 7)) << 4)) | (edge << 16);
-      plin[i] = ph * g.W + pw;
+      plin[i] = (uint32_t)(ph * g.W + pw);
     }
     // cursor over the GroupNorm-folded operand loads of this CTA, in the order the MMA warp consumes them
     struct Cur { int w, e; Ring ring; Tile t; bool valid; };
@@ -401,12 +394,12 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     auto edges_of = [&](const Tile& t) -> uint32_t {   // image borders the tile touches (+ "beyond the patch")
       return ((t.h0 == 0 ? 1u : 0u) | (t.h0 + 16 == g.H ? 2u : 0u) | (t.w0 == 0 ? 4u : 0u) | (t.w0 + 8 == g.W ? 8u : 0u) | 16u) << 16;
     };
-    auto src_of = [&](const Cur& c, const KEnt3& en, int& Cs) -> const uint8_t* {
+    auto src_of = [&](const Cur& c, const KEnt3& en, uint32_t& Cs) -> const uint8_t* {
       // (constant-index selects: a dynamically indexed kernel parameter array is copied to local memory)
       const void* sp = en.seg == 0 ? ep.gn_src[0] : (en.seg == 1 ? ep.gn_src[1] : ep.gn_src[2]);
-      Cs = en.seg == 0 ? ep.gn_C[0] : (en.seg == 1 ? ep.gn_C[1] : ep.gn_C[2]);
+      Cs = (uint32_t)(en.seg == 0 ? ep.gn_C[0] : (en.seg == 1 ? ep.gn_C[1] : ep.gn_C[2]));
       const long long pix0 = ((long long)c.t.n0 * g.H + (c.t.h0 - 1)) * g.W + (c.t.w0 - 1);
-      return reinterpret_cast<const uint8_t*>(sp) + (pix0 * Cs + en.c0 + ch8 * 8) * 2;
+      return reinterpret_cast<const uint8_t*>(sp) + (pix0 * (long long)Cs + en.c0 + ch8 * 8) * 2;
     };
     auto load_affine = [&](const Cur& c, const KEnt3& en) {
       if (c.t.n0 >= B) return;
@@ -421,16 +414,19 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     };
     auto load_patch = [&](const Cur& c, uint4 (&buf)[XF_PIX]) {
       const KEnt3 en = tab[c.e];
-      int Cs;
+      uint32_t Cs;
       const uint8_t* src = src_of(c, en, Cs);
-      const uint32_t te = c.t.n0 < B ? edges_of(c.t) : 0xffffffffu;
+      const uint32_t te = (c.t.n0 < B && !(ep.hack & 4)) ? edges_of(c.t) : 0xffffffffu;
+      const uint32_t cs2 = Cs * 2u;          // pixel pitch in bytes; plin * cs2 < 2^32 (one image plane of <= 2048 channels)
 #pragma unroll
       for (int i = 0; i < XF_PIX; ++i)
-        if (!(ptab[i] & te)) buf[i] = __ldg(reinterpret_cast<const uint4*>(src + (long long)plin[i] * Cs * 2));
+        if (!(ptab[i] & te)) buf[i] = __ldg(reinterpret_cast<const uint4*>(src + (unsigned long long)plin[i] * cs2));
     };
-    long long tr_xb = 0;
+    long long tr_xb = 0, tr_xw = 0;
     // transform the patch in `buf` (cursor `cur`) while the loads of the next one (`nxt`) are in flight in `bufn`
+    long long tr_xp = 0;
     auto step = [&](Cur& cur, uint4 (&buf)[XF_PIX], uint4 (&bufn)[XF_PIX]) {
+      const long long t_p0 = TRACE ? clock64() : 0;
       const KEnt3 en = tab[cur.e];
       const bool silu = en.gn == 2;
       const uint32_t te = cur.t.n0 < B ? edges_of(cur.t) : 0xffffffffu;
@@ -447,7 +443,8 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         load_affine(nxt, tab[nxt.e]);
         load_patch(nxt, bufn);
       }
-      tc::mbar_wait(&g_empty[cur.ring.i], cur.ring.ph ^ 1);       // the MMAs that read this stage have retired
+      if (TRACE) tr_xp += clock64() - t_p0;
+      { TRACE_T0(); tc::mbar_wait(&g_empty[cur.ring.i], cur.ring.ph ^ 1); TRACE_ACC(tr_xw); }   // the MMAs that read this stage have retired
       const long long t_b0 = TRACE ? clock64() : 0;
       uint8_t* st = smem_g + cur.ring.i * A_STAGE;
       // one bf16 pair: affine (+ SiLU) in fp32, back to bf16
@@ -473,7 +470,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         const bool in_img = !(ptab[i] & te);
         if (in_img) v = buf[i];
-        if (in_img) {
+        if (in_img && !(ep.hack & 8)) {
           v.x = xf2(v.x, a0.x, b0.x, a0.y, b0.y, silu);
           v.y = xf2(v.y, a0.z, b0.z, a0.w, b0.w, silu);
           v.z = xf2(v.z, a1.x, b1.x, a1.y, b1.y, silu);
@@ -493,12 +490,16 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       load_affine(cur, tab[cur.e]);
       load_patch(cur, bufa);
     }
+    long long tr_xl = 0;
     while (cur.valid) {
       step(cur, bufa, bufb);
+      TRACE_T0();
 #pragma unroll
       for (int i = 0; i < XF_PIX; ++i) bufa[i] = bufb[i];
+      if (TRACE) { asm volatile("" :: "r"(bufa[0].x), "r"(bufa[XF_PIX - 1].w) : "memory"); }
+      TRACE_ACC(tr_xl);
     }
-    if (TRACE && xt == 0) trace_put(ep, 7, tr_xb);
+    if (TRACE && xt == 0) { trace_put(ep, 7, tr_xb); trace_put(ep, 9, tr_xw); trace_put(ep, 10, tr_xl); trace_put(ep, 11, tr_xp); }
 #undef EO_LOAD_AFFINE
   } else if (warp >= EPI_WARP0) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
@@ -628,26 +629,6 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             for (int e2 = 0; e2 < 4; ++e2) h2[e2] = __floats2bfloat162_rn(f[k * 8 + e2 * 2], f[k * 8 + e2 * 2 + 1]);
             *reinterpret_cast<uint4*>(stg + row_off + ((((uint32_t)(half * 4 + k)) ^ swz) << 4)) = o;
           }
-          if (do_stats && warp_valid && n < Cout) {
-            // per-channel sum and sum of squares of this warp's 32 pixel rows (GroupNorm statistics of
-            // the tensor being written, from the fp32 values; reduced per group by k_gn_finalize_ch).
-            // Deterministic: fixed-order fp32 partial sums; only the cross-tile accumulation is atomic,
-            // and that one is in double.
-            float sq[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
-            const float cs = warp_column_sums(f, lane);
-            const float cq = warp_column_sums(sq, lane);
-            const int col = c * 64 + half * 32 + lane;
-            if (single_image) {
-              sstat[(q * 256 + col) * 2] = cs;
-              sstat[(q * 256 + col) * 2 + 1] = cq;
-            } else {
-              double* dst = ep.stats + ((long long)n_img * Cout + n + lane) * 2;
-              atomicAdd(dst, (double)cs);
-              atomicAdd(dst + 1, (double)cq);
-            }
-          }
         }
         if (has_res) {
           __syncwarp();
@@ -660,6 +641,32 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           bulk_commit();
         }
         __syncwarp();
+        if (do_stats && warp_valid) {
+          // GroupNorm statistics of the tensor being written: per-channel sum and sum of squares of this warp's 32
+          // pixel rows, read back from the bf16 staging rows the TMA store is draining (the values the consumer will
+          // normalise).  Lane l owns channels 2l, 2l+1 of the chunk: one conflict-free 4-byte column read per row,
+          // 32 rows in fixed order -- 7 instructions per row in a rolled loop, against 62 shuffles + 124 selects per
+          // 32 columns for the register-resident column sums it replaces (k_gn_finalize_ch reduces per group).
+          // Deterministic: fixed-order fp32 partial sums; only the cross-tile accumulation is atomic, and in double.
+          const uint32_t cchunk = (uint32_t)lane >> 2, csub = ((uint32_t)lane & 3u) * 4u;
+          const uint8_t* srow = stg + row0 * 128 + csub;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 4
+          for (uint32_t r = 0; r < 32; ++r) {
+            const uint32_t wv = *reinterpret_cast<const uint32_t*>(srow + r * 128u + ((cchunk ^ (r & 7u)) << 4));
+            const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
+            s0 += x0; s1 += x1;
+            q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
+          }
+          const int col = c * 64 + 2 * lane;
+          if (single_image) {
+            *reinterpret_cast<float4*>(sstat + (q * 256 + col) * 2) = make_float4(s0, q0, s1, q1);
+          } else if (t.nbase + col < Cout) {
+            double* dst = ep.stats + ((long long)n_img * Cout + t.nbase + col) * 2;
+            atomicAdd(dst, (double)s0); atomicAdd(dst + 1, (double)q0);
+            atomicAdd(dst + 2, (double)s1); atomicAdd(dst + 3, (double)q1);
+          }
+        }
       }
       if (do_stats && single_image) {
         asm volatile("bar.sync 1, 256;" ::: "memory");      // all eight epilogue warps
@@ -736,6 +743,7 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
              "tc_conv3: fused GroupNorm statistics need at least 32 pixels per image (%dx%d)", p.H, p.W);
   EO_REQUIRE(!p.out_f32 && !p.res_f32, EO_ERR_ARG, "tc_conv3: bf16 outputs and residuals only");
   g.tiles_w = p.W / g.bw; g.tiles_h = p.H / g.bh;
+  g.d_tw.set((unsigned)g.tiles_w); g.d_th.set((unsigned)g.tiles_h);
   pl->g3 = g;
   int BN = 64;
   for (int cand : {256, 192, 128, 64}) if (p.Cout % cand == 0) { BN = cand; break; }
@@ -824,19 +832,25 @@ void tc_conv3_set_trace(long long* dev_buf, int n) { g_trace3 = dev_buf; g_trace
 int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
   static bool attr_set = false;
   const TcConvParams& p = pl->p;
-  const Geom3& g = pl->g3;
+  Geom3 g = pl->g3;
   const int BN = pl->bn_tile;
+  g.d_nt.set((unsigned)(p.Cout / BN));
   const bool has_res = p.residual != nullptr;
   const int b_bytes = (BN / 2) * 128;
   // operand-A stages: all three to whoever fills them, two each when a conv has both kinds of load
   bool any_gn = false, any_raw = false;
   for (int s = 0; s < p.nseg; ++s) { if (p.seg[s].gn_scale) any_gn = true; else any_raw = true; }
-  const int SAR = any_raw ? (any_gn ? 2 : 3) : 0, SAG = any_gn ? (any_raw ? 2 : 3) : 0;
+  int SAR = any_raw ? (any_gn ? 2 : 3) : 0, SAG = any_gn ? (any_raw ? 2 : 3) : 0;
+  if (const char* e = std::getenv("EO_SA")) {      // experiment: operand-A stages of a single-kind conv
+    const int v = atoi(e);
+    if (v >= 2 && v <= SA_MAX && !(any_gn && any_raw)) { if (any_raw) SAR = v; else SAG = v; }
+  }
   const int fixed = (SAR + SAG) * A_STAGE + Smem::VAR_OFF + (has_res ? 2 * STG_BYTES : 0);
   // narrow tiles: three weight tiles (one kernel row of a patch) per stage, see the MMA warp
   bool any_patch = false;
   for (int s = 0; s < p.nseg; ++s) any_patch |= p.seg[s].patch != 0;
-  const int TPB = (any_patch && BN <= 192) ? 3 : 1;
+  int TPB = (any_patch && BN <= 192) ? 3 : 1;
+  if (const char* e = std::getenv("EO_TPB")) { if (any_patch && (atoi(e) == 1 || atoi(e) == 3)) TPB = atoi(e); }
   const int b_stage = TPB * b_bytes;
   int SB = (SMEM_LIMIT - 1024 - fixed) / b_stage;
   if (SB > MAX_SB) SB = MAX_SB;
@@ -867,6 +881,8 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
     ep.any_gn |= on ? 1 : 0;
   }
   ep.trace = g_trace3; ep.trace_n = g_trace3_n;
+  ep.hack = (env_flag("EO_HACK_HALFB", false) ? 1 : 0) | (env_flag("EO_TRACE_EXT", false) ? 2 : 0) |
+            (env_flag("EO_HACK_NOLDG", false) ? 4 : 0) | (env_flag("EO_HACK_NOMATH", false) ? 8 : 0);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * ncl));
   cfg.blockDim = dim3(NUM_THREADS);

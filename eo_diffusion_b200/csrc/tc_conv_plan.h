@@ -21,10 +21,26 @@ struct TileGeom {
 //   the transform warps load the patch from global memory, apply it and write the operand stage;
 //   gnc = first channel of this load in the scale/shift rows
 struct KEnt3 { int seg, c0, dhw, dn, kofs, patch, gn, gnc; };   // dhw: dh in the low 16 bits, dw in the high
+// division by a launch-time constant as multiply-high + shift (exact for dividends below 2^31): the generic
+// integer division sequence is ~35 dependent instructions, and every warp role decodes a tile index per tile
+struct FastDiv {
+  unsigned d = 1, mul = 0, shr = 0;
+  void set(unsigned div) {
+    d = div; mul = 0; shr = 0;
+    if (div > 1) {
+      unsigned lg = 0;
+      while ((1u << lg) < div) ++lg;
+      const unsigned p = 31 + lg;
+      mul = (unsigned)(((1ull << p) + div - 1) / div);
+      shr = p - 32;
+    }
+  }
+};
 struct Geom3 {
   int bw, bh, bn;
   int tiles_w, tiles_h;
   int H, W;
+  FastDiv d_nt, d_tw, d_th;   // by n_ntiles, tiles_w, tiles_h
 };
 struct Epi3 {
   const float* bias;        // [Cout] or null
@@ -40,6 +56,7 @@ struct Epi3 {
   int any_gn;
   long long* trace;         // development aid: [n][8] per-CTA counters, or null
   int trace_n;
+  int hack;                // experiment: skip every second weight-stage load (WRONG results; timing only)
 };
 
 struct TcConvPlan {

@@ -26,12 +26,13 @@ def run(B, H, W, Cin, Cout, k, res):
                                                 B, H, W, Cin, Cout, k, _lib.stream_ptr()), "conv")
     call()
     torch.cuda.synchronize()
-    tr = torch.zeros((148, 8), dtype=torch.int64, device=dev)
+    tr = torch.zeros((296, 8), dtype=torch.int64, device=dev)
     L.eo_debug_conv_trace(_lib.ptr(tr), 148)
     call()
     torch.cuda.synchronize()
     L.eo_debug_conv_trace(None, 0)
-    t = tr.cpu().numpy()
+    full = tr.cpu().numpy()
+    t, ext = full[:148], full[148:]
     lead = t[t[:, 6] > 0]                       # leader CTAs carry the MMA warp's tile count
     tiles = np.median(lead[:, 6])
     f = lambda a, c: np.median(a[:, c]) / tiles
@@ -41,6 +42,10 @@ def run(B, H, W, Cin, Cout, k, res):
           f"(MMA floor {Cin * k * k / 64 * (256 if Cout % 256 else 512) / (1 if Cout % 256 else 1):.0f})\n"
           f"   per tile: MMA waits operands {f(lead, 1):.0f}, MMA waits accumulator {f(lead, 2):.0f}; epilogue waits accumulator "
           f"{f(allc, 3):.0f}, epilogue busy {f(allc, 4):.0f}; producer waits stages {f(lead, 5):.0f}; transform busy {f(allc, 7):.0f}")
+    if ext.any():
+        el = ext[t[:, 6] > 0]
+        print(f"   MMA waits on operand A alone {np.median(el[:, 0]) / tiles:.0f}; transform warps wait for a free stage "
+              f"{np.median(ext[t[:, 0] > 0][:, 1]) / tiles:.0f}, for the next patch's loads {np.median(ext[t[:, 0] > 0][:, 2]) / tiles:.0f}, before the stage wait {np.median(ext[t[:, 0] > 0][:, 3]) / tiles:.0f}")
 
 
 if __name__ == "__main__":

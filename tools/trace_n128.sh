@@ -1,7 +1,6 @@
-for gn in 0 2; do for st in 0 1; do
-echo "== GN=$gn STATS=$st"
-EO_TEST_GN=$gn EO_TEST_STATS=$st python tools/conv3_trace.py 64 256 256 128 128 3 0
-EO_TEST_GN=$gn EO_TEST_STATS=$st python tools/conv3_trace.py 64 256 256 128 128 3 1
-EO_TEST_GN=$gn EO_TEST_STATS=$st python tools/conv3_trace.py 64 256 256 384 128 3 0
-EO_TEST_GN=$gn EO_TEST_STATS=$st python tools/conv3_trace.py 64 128 128 256 256 3 0
-done; done
+export EO_TRACE_EXT=1
+run() { echo "== $*"; env "$@" EO_TEST_STATS=1 python tools/conv3_trace.py 64 256 256 128 128 3 0
+        env "$@" EO_TEST_STATS=1 python tools/conv3_trace.py 64 256 256 128 128 3 1
+        env "$@" EO_TEST_STATS=1 python tools/conv3_trace.py 64 256 256 384 128 3 0
+        env "$@" EO_TEST_STATS=1 python tools/conv3_trace.py 64 128 128 512 256 3 0; }
+run EO_TEST_GN=2
