@@ -74,12 +74,13 @@ typedef struct eo_unet_cfg {
   int32_t num_head_channels; /* -1 = use num_heads */
   int32_t num_heads_upsample; /* -1 = num_heads */
   int32_t use_new_attention_order;
-  /* options of the reference constructor that this path does not implement; they must
-     hold the values below or eo_unet_create fails with EO_ERR_ARG */
+  /* options of the reference constructor that this path does not implement (no configuration of the
+     reference sets them otherwise); they must hold the values below or eo_unet_create fails with EO_ERR_ARG */
   int32_t dims;                 /* 2 */
   int32_t conv_resample;        /* 1 */
-  int32_t use_scale_shift_norm; /* 0 */
-  int32_t resblock_updown;      /* 0 */
+  /* the switches of the reference's UNet / UNetBig / UNetSmall factories (unet_openai.py:783-922) */
+  int32_t use_scale_shift_norm; /* 0 | 1: FiLM conditioning, unet_openai.py:377-381 */
+  int32_t resblock_updown;      /* 0 | 1: up/down-sampling ResBlocks, unet_openai.py:366-371 */
 } eo_unet_cfg;
 
 EO_API int eo_unet_create(const eo_unet_cfg* cfg, eo_unet** out);
