@@ -445,7 +445,7 @@ def run_ours(args, wl):
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and kind == "sum":
-        sample_b, sample_steps = 1, 2
+        sample_b, sample_steps = 1, 10        # ~1 s per step on 16 host threads: 10-12 s of CPU work
         sec = cpu_reference_steps(size, sample_b, sample_steps, 1)
         cpu = {"value": sample_b / (T_DDPM * sec), "unit": "images/s", "cores": torch.get_num_threads(),
                "kind": "port", "ms_per_step": sec * 1e3,
