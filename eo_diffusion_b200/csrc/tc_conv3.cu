@@ -527,7 +527,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const uint8_t* rs = res_sm + set * STG_BYTES;
     const uint32_t tmem_empty_leader = tc::mapa_u32(tc::smem_u32(&tmem_empty[0]), 0);
     uint32_t it = 0, res_uses = 0;
-    long long tr_wait = 0, tr_busy = 0;
+    long long tr_wait = 0, tr_busy = 0, tr_e2 = 0, tr_e3 = 0, tr_e5 = 0, tr_e6 = 0;
     // Tiles inside one image (every halo-patch grid): bias[n] + bias_nc[image][n] of this warp's channels sit in a
     // warp-private shared-memory row, rebuilt only when the image or the channel tile changes -- the 16 global
     // loads per 32 columns they replace cost an L2 round trip each time (the L1 is all shared memory here).
@@ -576,11 +576,14 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           float f[32];
           {
             uint32_t v[32];                       // 32 columns at a time keeps the warp under 128 registers
+            TRACE_T0();
             tc::tmem_ld_32x32(taddr + half * 32, v);
             tc::tmem_ld_wait();
+            TRACE_ACC(tr_e2);
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           }
+          const long long t_e3 = TRACE ? clock64() : 0;
           if (half == 1 && c + 2 >= nchunks) {     // this warp's share of the accumulator now lives in registers
             tc::tc_fence_before();
             __syncwarp();
@@ -629,6 +632,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             for (int e2 = 0; e2 < 4; ++e2) h2[e2] = __floats2bfloat162_rn(f[k * 8 + e2 * 2], f[k * 8 + e2 * 2 + 1]);
             *reinterpret_cast<uint4*>(stg + row_off + ((((uint32_t)(half * 4 + k)) ^ swz) << 4)) = o;
           }
+          if (TRACE) tr_e3 += clock64() - t_e3;
         }
         if (has_res) {
           __syncwarp();
@@ -641,6 +645,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           bulk_commit();
         }
         __syncwarp();
+        const long long t_e5 = TRACE ? clock64() : 0;
         if (do_stats && warp_valid) {
           // GroupNorm statistics of the tensor being written: per-channel sum and sum of squares of this warp's 32
           // pixel rows, read back from the bf16 staging rows the TMA store is draining (the values the consumer will
@@ -650,11 +655,16 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           // Deterministic: fixed-order fp32 partial sums; only the cross-tile accumulation is atomic, and in double.
           const uint32_t cchunk = (uint32_t)lane >> 2, csub = ((uint32_t)lane & 3u) * 4u;
           const uint8_t* srow = stg + row0 * 128 + csub;
+          // all 32 reads are issued before the first is consumed: with the tensor core streaming operands out of the
+          // same shared memory a read takes ~200 clk (traced: 54 clk per row when issued four at a time)
+          uint32_t wv[32];
+#pragma unroll
+          for (uint32_t r = 0; r < 32; ++r)
+            wv[r] = *reinterpret_cast<const uint32_t*>(srow + r * 128u + ((cchunk ^ (r & 7u)) << 4));
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 4
+#pragma unroll
           for (uint32_t r = 0; r < 32; ++r) {
-            const uint32_t wv = *reinterpret_cast<const uint32_t*>(srow + r * 128u + ((cchunk ^ (r & 7u)) << 4));
-            const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
+            const float x0 = __uint_as_float(wv[r] << 16), x1 = __uint_as_float(wv[r] & 0xffff0000u);
             s0 += x0; s1 += x1;
             q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
           }
@@ -667,7 +677,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             atomicAdd(dst + 2, (double)s1); atomicAdd(dst + 3, (double)q1);
           }
         }
+        if (TRACE) tr_e5 += clock64() - t_e5;
       }
+      const long long t_e6 = TRACE ? clock64() : 0;
       if (do_stats && single_image) {
         asm volatile("bar.sync 1, 256;" ::: "memory");      // all eight epilogue warps
         if (t.n0 < B) {
@@ -681,11 +693,14 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");      // sstat is rewritten by the next tile
       }
-      if (TRACE) tr_busy += clock64() - t_busy0;
+      if (TRACE) { tr_e6 += clock64() - t_e6; tr_busy += clock64() - t_busy0; }
     }
     if (lane == 0) bulk_wait0();
     __syncwarp();
-    if (TRACE && et == 0) { trace_put(ep, 3, tr_wait); trace_put(ep, 4, tr_busy); }
+    if (TRACE && et == 0) {
+      trace_put(ep, 3, tr_wait); trace_put(ep, 4, tr_busy);
+      trace_put(ep, 12, tr_e2); trace_put(ep, 13, tr_e3); trace_put(ep, 14, tr_e5); trace_put(ep, 15, tr_e6);
+    }
     tc::tc_fence_before();
   }
   __syncwarp();

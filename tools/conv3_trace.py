@@ -46,6 +46,9 @@ def run(B, H, W, Cin, Cout, k, res):
         el = ext[t[:, 6] > 0]
         print(f"   MMA waits on operand A alone {np.median(el[:, 0]) / tiles:.0f}; transform warps wait for a free stage "
               f"{np.median(ext[t[:, 0] > 0][:, 1]) / tiles:.0f}, for the next patch's loads {np.median(ext[t[:, 0] > 0][:, 2]) / tiles:.0f}, before the stage wait {np.median(ext[t[:, 0] > 0][:, 3]) / tiles:.0f}")
+        ea = ext[t[:, 0] > 0]
+        print(f"   epilogue warp 0: tcgen05.ld + wait {np.median(ea[:, 4]) / tiles:.0f}, bias/residual/pack/stage {np.median(ea[:, 5]) / tiles:.0f}, "
+              f"statistics read-back {np.median(ea[:, 6]) / tiles:.0f}, combine + barriers {np.median(ea[:, 7]) / tiles:.0f}")
 
 
 if __name__ == "__main__":
