@@ -227,7 +227,22 @@ static bool use_pairs() {
   return v != 0;
 }
 
+// 128-pixel tile of a plain (non-patch) operand: bw x bh pixels of bn images, every extent a power of two that
+// divides the feature map (24 x 24 -> 8 x 8 x 2, 12 x 12 -> 4 x 4 x 8, 48 x 32 -> 16 x 8 x 1)
+void tc_conv_tile_geom(int H, int W, int* bw, int* bh, int* bn) {
+  int w = W & -W;                       // largest power of two dividing W
+  if (w > 16) w = 16;
+  int h = H & -H;
+  if (h > BM / w) h = BM / w;
+  *bw = w; *bh = h; *bn = BM / (w * h);
+}
+
 bool tc_conv_stats_supported(int H, int W) {
+  if (tc_conv3_enabled()) {
+    int bw, bh, bn;
+    tc_conv_tile_geom(H, W, &bw, &bh, &bn);
+    return bw * bh >= 32;
+  }
   int bw = floor_pow2(W < 16 ? W : 16);
   int bh = floor_pow2(H < BM / bw ? H : BM / bw);
   return bw * bh >= 32;

@@ -737,7 +737,6 @@ bool tc_conv_patch_supported(int H, int W) {
   return tc_conv3_enabled() && v != 0 && H % 16 == 0 && W % 8 == 0;
 }
 
-static int floor_pow2_(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
 
 int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
   Geom3 g;
@@ -748,9 +747,7 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
     EO_REQUIRE(p.H % 16 == 0 && p.W % 8 == 0, EO_ERR_ARG, "tc_conv3: halo patches need H %% 16 == 0 and W %% 8 == 0 (%dx%d)", p.H, p.W);
     g.bw = 8; g.bh = 16; g.bn = 1;
   } else {
-    g.bw = floor_pow2_(p.W < 16 ? p.W : 16);
-    g.bh = floor_pow2_(p.H < BM / g.bw ? p.H : BM / g.bw);
-    g.bn = BM / (g.bw * g.bh);
+    tc_conv_tile_geom(p.H, p.W, &g.bw, &g.bh, &g.bn);
   }
   EO_REQUIRE(p.W % g.bw == 0 && p.H % g.bh == 0, EO_ERR_ARG, "tc_conv3: feature map %dx%d is not tileable by %dx%d boxes",
              p.H, p.W, g.bh, g.bw);

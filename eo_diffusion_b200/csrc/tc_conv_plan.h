@@ -74,6 +74,7 @@ struct TcConvPlan {
 };
 
 bool tc_conv3_enabled();
+void tc_conv_tile_geom(int H, int W, int* bw, int* bh, int* bn);
 int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl);
 int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st);
 void tc_conv3_set_trace(long long* dev_buf, int n_ctas);

@@ -37,6 +37,14 @@ def _conv_case(dev, B, H, W, Cin, Cout, k, with_res, seed):
     (3, 8, 8, 64, 64, 3, False),        # odd batch: partially filled tile
     (1, 32, 32, 256, 256, 3, True),     # BN = 256 variant
     (1, 64, 64, 128, 384, 3, False),
+    # tile grids that are not powers of two (tile decode by multiply-high): 3 x 3, 6 x 5 and 3 x 7 tiles of 16 x 8 pixels,
+    # an odd number of tiles (all-masked partner), several images
+    (2, 48, 24, 64, 128, 3, False),
+    (1, 96, 40, 128, 128, 3, True),
+    (3, 48, 56, 64, 192, 3, False),
+    (5, 48, 32, 128, 256, 1, True),
+    (3, 24, 24, 128, 256, 1, True),     # 8 x 8 pixels of two images per tile
+    (9, 12, 12, 64, 128, 3, False),     # 4 x 4 pixels of eight images per tile, plain 3x3 taps
     (2, 32, 32, 1024, 512, 3, False),   # deepest K of the BASELINE UNet (144 K blocks)
 ])
 def test_conv_tc(cuda_dev, B, H, W, Cin, Cout, k, res):

@@ -91,6 +91,25 @@ def test_batch_independence_and_replanning(cuda_dev, mode):
     assert rel_l2(again, one) <= tol
 
 
+@pytest.mark.parametrize("mode,size,batch", [("fp32", 48, 2), ("bf16", 48, 3), ("bf16", 96, 1)])
+def test_non_power_of_two_image(cuda_dev, mode, size, batch):
+    """48 x 48 and 96 x 96 inputs: feature maps of 48 / 24 / 12 (96 / 48 / 24 / 12) pixels a side, i.e. tile grids that
+    are not powers of two, maps that take the halo-patch path and maps that do not, odd tile counts.  Against
+    the oracle evaluated here on the same weights."""
+    cfg = dict(image_size=size, in_channels=3, model_channels=64, out_channels=3, num_res_blocks=1,
+               attention_resolutions=[2, 4], channel_mult=[1, 2, 2], num_heads=2)
+    m = build_unet(cfg, 91, 92)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    gen = torch.Generator().manual_seed(size + batch)
+    x = torch.randn((batch, 3, size, size), generator=gen)
+    t = torch.tensor([999, 3, 500][:batch])
+    want = O.unet_forward(sd, O.full_cfg(**cfg), x, t)
+    got = m.to(cuda_dev).set_compute_mode(mode)(x.to(cuda_dev), t.to(cuda_dev))
+    err = rel_l2(got, want)
+    print(f"[parity] {mode} {size}x{size} batch {batch}: eps rel L2 {err:.3e}")
+    assert err <= (TOL["fp32"] if mode == "fp32" else TOL_BF16_NARROW)
+
+
 def test_class_conditional_and_new_attention_order(cuda_dev):
     """label_emb add (unet_openai.py:764-766), num_head_channels, QKVAttention channel order
     (:497-515) against the oracle on random weights."""
