@@ -67,7 +67,7 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 2^x on the FMA pipe (k_attn_tc5 takes every fourth pair of exponentials off the MUFU pipe, its limiter):
+// 2^x on the FMA pipe (k_attn_tc5 takes every third pair of exponentials off the MUFU pipe, its limiter):
 // x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (relative error 7.5e-5,
 // 26 times below the bf16 rounding of P), 2^n added into the exponent field.  x <= 127 - 1; below -125 clamps.
 __device__ __forceinline__ float ex2_fma(float x) {
@@ -78,6 +78,32 @@ __device__ __forceinline__ float ex2_fma(float x) {
   p = fmaf(p, f, 0.6932609677314758f);
   p = fmaf(p, f, 0.9999280571937561f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2: one issue slot for two lanes' worth of a pair): the scale / subtract of
+// every logit pair and the polynomial form of 2^x run on these, halving the issue slots they take next to the MUFU pipe.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// ex2_fma of a pair (same arithmetic, element for element)
+__device__ __forceinline__ void ex2_fma2(uint64_t x, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  x = pack2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const uint64_t t = add2(x, pack2(12582912.0f, 12582912.0f));
+  const uint64_t r = add2(t, pack2(-12582912.0f, -12582912.0f));
+  const uint64_t f = fma2(r, pack2(-1.0f, -1.0f), x);
+  uint64_t p = fma2(pack2(0.0551716685295105f, 0.0551716685295105f), f, pack2(0.2426111251115799f, 0.2426111251115799f));
+  p = fma2(p, f, pack2(0.6932609677314758f, 0.6932609677314758f));
+  p = fma2(p, f, pack2(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  unpack2(p, q0, q1);
+  unpack2(t, t0, t1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
@@ -405,10 +431,14 @@ constexpr int N_BARS5 = 1 + 2 * KV_STAGES5 + 6 * NT5;
 constexpr int ATTN5_SMEM = OFF5_BAR + N_BARS5 * 8 + 16 + 1024;
 constexpr int ATTN5_THREADS = 768;
 constexpr int SM_WARP0 = 8;
-#ifndef EO_ATTN_POLY_EVERY
-#define EO_ATTN_POLY_EVERY 4
+// POLY_NUM of every POLY_DEN pairs of exponentials run on the FMA pipe (0 = none)
+#ifndef EO_ATTN_POLY_NUM
+#define EO_ATTN_POLY_NUM 1
 #endif
-constexpr int POLY_EVERY = EO_ATTN_POLY_EVERY;   // every n-th pair of exponentials runs on the FMA pipe (0 = none)
+#ifndef EO_ATTN_POLY_DEN
+#define EO_ATTN_POLY_DEN 3
+#endif
+constexpr int POLY_NUM = EO_ATTN_POLY_NUM, POLY_DEN = EO_ATTN_POLY_DEN;
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t v[16]) {
   asm volatile(
@@ -613,13 +643,19 @@ k_attn_tc5(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
         }
         if (TRACE) { const long long c = clock64(); tr_max += c - tq0; tq0 = c; }
         float rs0 = 0.f, rs1 = 0.f;
+        const uint64_t sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m, -m);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float x0 = fmaf(__uint_as_float(v[2 * k]), scale_log2, -m);
-          const float x1 = fmaf(__uint_as_float(v[2 * k + 1]), scale_log2, -m);
-          const bool on_fma = POLY_EVERY > 0 && (k % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == (POLY_EVERY - 1);
-          const float p0 = on_fma ? ex2_fma(x0) : ex2(x0);
-          const float p1 = on_fma ? ex2_fma(x1) : ex2(x1);
+          const uint64_t x = fma2(pack2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), sc2, nm2);
+          const bool on_fma = POLY_NUM > 0 && ((k * POLY_NUM) % POLY_DEN) < POLY_NUM;
+          float p0, p1;
+          if (on_fma) {
+            ex2_fma2(x, p0, p1);
+          } else {
+            float x0, x1;
+            unpack2(x, x0, x1);
+            p0 = ex2(x0); p1 = ex2(x1);
+          }
           if (!LSUM_MMA) { rs0 += p0; rs1 += p1; }
           __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
           pk[k] = *reinterpret_cast<uint32_t*>(&h2);
