@@ -82,12 +82,7 @@ __device__ __forceinline__ float ex2_fma(float x) {
 
 // Packed fp32 pairs (Blackwell FFMA2 / FADD2: one issue slot for two lanes' worth of a pair): the scale / subtract of
 // every logit pair and the polynomial form of 2^x run on these, halving the issue slots they take next to the MUFU pipe.
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+using tc::pack2; using tc::unpack2; using tc::fma2; using tc::add2;
 // ex2_fma of a pair (same arithmetic, element for element)
 __device__ __forceinline__ void ex2_fma2(uint64_t x, float& p0, float& p1) {
   float x0, x1;

@@ -433,10 +433,11 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       // scale / shift of this thread's 8 channels.  With SiLU they are halved: silu(y) = h + h tanh(h),
       // h = y/2 (common.cuh silu_f), and 0.5 * fma(x, s, b) == fma(x, 0.5 s, 0.5 b) exactly.
       const float hf = silu ? 0.5f : 1.0f;
-      const float4 a0 = make_float4(na0.x * hf, na0.y * hf, na0.z * hf, na0.w * hf);
-      const float4 a1 = make_float4(na1.x * hf, na1.y * hf, na1.z * hf, na1.w * hf);
-      const float4 b0 = make_float4(nb0.x * hf, nb0.y * hf, nb0.z * hf, nb0.w * hf);
-      const float4 b1 = make_float4(nb1.x * hf, nb1.y * hf, nb1.z * hf, nb1.w * hf);
+      // (packed fp32 pairs: FFMA2 does the affine and the SiLU recombination of a bf16 pair in one issue slot each)
+      const uint64_t a01 = tc::pack2(na0.x * hf, na0.y * hf), a23 = tc::pack2(na0.z * hf, na0.w * hf);
+      const uint64_t a45 = tc::pack2(na1.x * hf, na1.y * hf), a67 = tc::pack2(na1.z * hf, na1.w * hf);
+      const uint64_t b01 = tc::pack2(nb0.x * hf, nb0.y * hf), b23 = tc::pack2(nb0.z * hf, nb0.w * hf);
+      const uint64_t b45 = tc::pack2(nb1.x * hf, nb1.y * hf), b67 = tc::pack2(nb1.z * hf, nb1.w * hf);
       Cur nxt = cur;
       seek(nxt, false);
       if (nxt.valid) {
@@ -448,16 +449,15 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       const long long t_b0 = TRACE ? clock64() : 0;
       uint8_t* st = smem_g + cur.ring.i * A_STAGE;
       // one bf16 pair: affine (+ SiLU) in fp32, back to bf16
-      auto xf2 = [&](uint32_t in, float s0, float h0, float s1, float h1, bool act) -> uint32_t {
-        float x0 = __uint_as_float(in << 16), x1 = __uint_as_float(in & 0xffff0000u);
-        x0 = fmaf(x0, s0, h0);
-        x1 = fmaf(x1, s1, h1);
+      auto xf2 = [&](uint32_t in, uint64_t sc, uint64_t sh, bool act) -> uint32_t {
+        uint64_t x = tc::fma2(tc::pack2(__uint_as_float(in << 16), __uint_as_float(in & 0xffff0000u)), sc, sh);
+        float x0, x1;
+        tc::unpack2(x, x0, x1);
         if (act) {
           float t0, t1;
           asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(x0));
           asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(x1));
-          x0 = fmaf(x0, t0, x0);
-          x1 = fmaf(x1, t1, x1);
+          tc::unpack2(tc::fma2(x, tc::pack2(t0, t1), x), x0, x1);
         }
         __nv_bfloat162 o = __floats2bfloat162_rn(x0, x1);
         return *reinterpret_cast<uint32_t*>(&o);
@@ -471,10 +471,10 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         const bool in_img = !(ptab[i] & te);
         if (in_img) v = buf[i];
         if (in_img && !(ep.hack & 8)) {
-          v.x = xf2(v.x, a0.x, b0.x, a0.y, b0.y, silu);
-          v.y = xf2(v.y, a0.z, b0.z, a0.w, b0.w, silu);
-          v.z = xf2(v.z, a1.x, b1.x, a1.y, b1.y, silu);
-          v.w = xf2(v.w, a1.z, b1.z, a1.w, b1.w, silu);
+          v.x = xf2(v.x, a01, b01, silu);
+          v.y = xf2(v.y, a23, b23, silu);
+          v.z = xf2(v.z, a45, b45, silu);
+          v.w = xf2(v.w, a67, b67, silu);
         }
         *reinterpret_cast<uint4*>(st + (ptab[i] & 0xffffu)) = v;    // zeros outside the image
       }
