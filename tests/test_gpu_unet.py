@@ -18,8 +18,8 @@ pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 1e-4, "bf16": 1e-2}
 # The 1e-2 bf16 bound of BASELINE.json is stated for the benchmark UNet (base width 128): there the
-# measured error is 7.5e-3 to 7.9e-3 at every t.  The 64-wide synthetic nets ("small*") average each
-# bf16 rounding over half as many channels and land at 0.97e-2 to 1.05e-2; a CPU emulation of the
+# measured error is 8.2e-3 to 8.5e-3 at every t.  The 64-wide synthetic nets ("small*") average each
+# bf16 rounding over half as many channels and land at 1.03e-2 to 1.12e-2; a CPU emulation of the
 # rounding sites (DESIGN.md "bf16 error budget") attributes it to the bf16 residual stream (6.2e-3),
 # bf16 weights (5.0e-3) and the bf16 MMA operands (3-3.6e-3 each), i.e. to bf16 itself, not to a
 # kernel defect -- so those two fixtures are held to 1.25e-2.
