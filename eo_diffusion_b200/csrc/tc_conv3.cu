@@ -114,7 +114,7 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ void trace_put(const Epi3& ep, int slot, long long v) {
   if (!ep.trace || (int)blockIdx.x >= ep.trace_n) return;
   if (slot < 8) ep.trace[(long long)blockIdx.x * 8 + slot] = v;
-  else if (ep.hack & 2) ep.trace[((long long)ep.trace_n + blockIdx.x) * 8 + slot - 8] = v;
+  else if (ep.trace_ext) ep.trace[((long long)ep.trace_n + blockIdx.x) * 8 + slot - 8] = v;
 }
 #define TRACE_T0() const long long _t0 = TRACE ? clock64() : 0
 #define TRACE_ACC(var) do { if (TRACE) (var) += clock64() - _t0; } while (0)
@@ -201,7 +201,6 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     // ------------------------------------------------------------------ operand producer
     Ring ra, rb;
     long long tr_wait = 0;
-    uint32_t hk = 0;
     const uint32_t r_full_l = tc::mapa_u32(tc::smem_u32(&r_full[0]), 0);   // the leader's barriers
     const uint32_t b_full_l = tc::mapa_u32(tc::smem_u32(&b_full[0]), 0);
     const int b_row = (int)rank * (BN / 2);
@@ -234,9 +233,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         const int per = en.patch ? TPB : 1;
         for (int j = 0; j < nb; j += per) {
           { TRACE_T0(); tc::mbar_wait(&b_empty[rb.i], rb.ph ^ 1); TRACE_ACC(tr_wait); }
-          const bool skip = (ep.hack & 1) && ((hk++) & 1);
-          if (skip) { if (rank == 0 && tc::elect_one()) tc::mbar_arrive(&b_full[rb.i]); }
-          else if (tc::elect_one()) {
+          if (tc::elect_one()) {
             // one arrival per phase: the leader's producer, which posts the byte count of BOTH CTAs'
             // loads; the peer's TMA only completes transactions on the leader's barrier
             if (rank == 0) tc::mbar_arrive_expect_tx(&b_full[rb.i], 2 * per * b_bytes);
@@ -416,7 +413,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       const KEnt3 en = tab[c.e];
       uint32_t Cs;
       const uint8_t* src = src_of(c, en, Cs);
-      const uint32_t te = (c.t.n0 < B && !(ep.hack & 4)) ? edges_of(c.t) : 0xffffffffu;
+      const uint32_t te = c.t.n0 < B ? edges_of(c.t) : 0xffffffffu;
       const uint32_t cs2 = Cs * 2u;          // pixel pitch in bytes; plin * cs2 < 2^32 (one image plane of <= 2048 channels)
 #pragma unroll
       for (int i = 0; i < XF_PIX; ++i)
@@ -470,7 +467,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         const bool in_img = !(ptab[i] & te);
         if (in_img) v = buf[i];
-        if (in_img && !(ep.hack & 8)) {
+        if (in_img) {
           v.x = xf2(v.x, a01, b01, silu);
           v.y = xf2(v.y, a23, b23, silu);
           v.z = xf2(v.z, a45, b45, silu);
@@ -893,8 +890,7 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
     ep.any_gn |= on ? 1 : 0;
   }
   ep.trace = g_trace3; ep.trace_n = g_trace3_n;
-  ep.hack = (env_flag("EO_HACK_HALFB", false) ? 1 : 0) | (env_flag("EO_TRACE_EXT", false) ? 2 : 0) |
-            (env_flag("EO_HACK_NOLDG", false) ? 4 : 0) | (env_flag("EO_HACK_NOMATH", false) ? 8 : 0);
+  ep.trace_ext = env_flag("EO_TRACE_EXT", false) ? 1 : 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * ncl));
   cfg.blockDim = dim3(NUM_THREADS);

@@ -56,7 +56,7 @@ struct Epi3 {
   int any_gn;
   long long* trace;         // development aid: [n][8] per-CTA counters, or null
   int trace_n;
-  int hack;                // experiment: skip every second weight-stage load (WRONG results; timing only)
+  int trace_ext;           // development aid: the trace buffer holds 2 * trace_n * 8 counters (slots 8..15 in use)
 };
 
 struct TcConvPlan {
