@@ -1574,4 +1574,31 @@ int eo_test_attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int
   return rc;
 }
 
+// EODiffusion.sampling's loop (diffusion/model.py:46-75) over the per-step entry points
+int eo_sample_ddpm(eo_unet* u, float* x, const float* noise_tape, const float* gt, const float* mask, const float* cond,
+                   int Cc, const int64_t* y, const int64_t* timestep_rows, const float* table, float* eps_scratch,
+                   int T, int B, int Cx, int H, int W, int clip, void* stream) {
+  EO_REQUIRE(u && x && noise_tape && timestep_rows && table && eps_scratch, EO_ERR_ARG, "eo_sample_ddpm: null argument");
+  EO_REQUIRE(T >= 1 && B >= 1 && Cx >= 1 && H >= 1 && W >= 1, EO_ERR_ARG, "eo_sample_ddpm: bad extents");
+  EO_REQUIRE((gt == nullptr) == (mask == nullptr), EO_ERR_ARG, "eo_sample_ddpm: 'sum' conditioning needs gt and mask");
+  const int HW = H * W;
+  const size_t n = (size_t)B * Cx * HW;
+  int rc;
+  if (gt && (rc = eo_ddpm_sum_mix(x, gt, mask, noise_tape, timestep_rows + (size_t)(T - 1) * B, table, x, B, Cx, HW, stream)))
+    return rc;
+  for (int i = T - 1; i >= 0; --i) {
+    const int k = T - 1 - i;
+    const int64_t* t = timestep_rows + (size_t)i * B;
+    if ((rc = eo_unet_forward(u, x, Cx, cond, Cc, t, y, eps_scratch, B, stream))) return rc;
+    const float* noise = noise_tape + (size_t)k * n;
+    if (gt && i > 0)
+      rc = eo_ddpm_step_mix(x, eps_scratch, noise, t, gt, mask, noise + n, timestep_rows + (size_t)(i - 1) * B, table, x, B, Cx,
+                            HW, clip, 1, stream);
+    else
+      rc = eo_ddpm_step(x, eps_scratch, noise, t, table, x, B, Cx, HW, clip, i > 0 ? 1 : 0, stream);
+    if (rc) return rc;
+  }
+  return EO_OK;
+}
+
 }  // extern "C"

@@ -181,6 +181,23 @@ EO_API int eo_ddpm_step_mix(const float* x_t, const float* eps, const float* noi
                      float* x_out, int B, int C, int HW, int clip, int all_t_positive,
                      void* stream);
 
+/* The whole DDPM trajectory in one call: the loop of EODiffusion.sampling (diffusion/model.py:46-75) without its
+ * PNG side effect and with the reference's random draws handed in as a tape, so a C caller needs no per-step round trip.
+ *   x             [B, Cx, H, W]: in x_T, out x_0 (un-normalised, like the reference's return value)
+ *   noise_tape    [T][B, Cx, H, W]: tape[k] = the k-th torch.randn_like draw (k = 0 drives iteration i = T-1; in 'sum'
+ *                 mode the same draw forward-diffuses gt, model.py:57-59)
+ *   gt, mask      'sum' conditioning ([B, Cx, H, W], [B, 1, H, W]) or both NULL
+ *   cond, Cc      concat conditioning ([B, Cc, H, W]) or NULL, 0
+ *   y             [B] int64 class labels or NULL
+ *   timestep_rows [T][B] int64, row i = the value i repeated (what the reference builds with torch.tensor([i] * n))
+ *   table         [T][EO_DDPM_NCOEF], see above
+ *   eps_scratch   [B, out_channels, H, W] work buffer for the UNet output
+ * Same kernels in the same order as the per-step entry points: bit-identical to driving them from the host. */
+EO_API int eo_sample_ddpm(eo_unet* u, float* x, const float* noise_tape, const float* gt, const float* mask,
+                   const float* cond, int Cc, const int64_t* y, const int64_t* timestep_rows,
+                   const float* table, float* eps_scratch, int T, int B, int Cx, int H, int W, int clip,
+                   void* stream);
+
 /* ------------------------------------------------------------------------------------
  * DDIM step: replaces DDIMSampler.p_sample_ddim after the UNet call (diffusion/ddim.py:
  * 187-207).  Scalars are the fp32 values the reference materialises with torch.full:

@@ -254,3 +254,30 @@ def test_two_gpu_sharded_sampling_equals_single_gpu(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_two_rank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").read_text() == "1" and (tmp_path / "ok1").read_text() == "1"
+
+
+@pytest.mark.parametrize("sum_mode,clip", [(True, True), (False, False)])
+def test_whole_loop_entry_point_equals_host_loop(cuda_dev, sum_mode, clip):
+    """eo_sample_ddpm (the whole trajectory in one C call, noise handed in as a tape) runs the same kernels in the
+    same order as EODiffusion.sampling driving the per-step entry points: bit-identical images."""
+    import ctypes as C
+    from eo_diffusion_b200 import _lib
+    g = golden("tiny_eps")
+    m, cfg = model_for(g, cuda_dev, "fp32")
+    T, n, size = 6, 2, int(cfg["image_size"])
+    diff = EODiffusion(m, size, 3, timesteps=T, cond_type="sum" if sum_mode else None).to(cuda_dev)
+    x_T, tape = O.noise_tape((n, 3, size, size), T, seed=21)
+    cond = O.synth_cond_sum(n, size, seed=22) if sum_mode else None
+    with replay([x_T], list(tape)):
+        want = diff.sampling(n, clipped_reverse_diffusion=clip, device=cuda_dev, cond=cond, write_pngs=False)
+    x = x_T.clone().to(cuda_dev).contiguous()
+    tape_d = torch.stack([t for t in tape]).to(cuda_dev).contiguous()
+    gt = cond[:, :3].contiguous().to(cuda_dev) if sum_mode else None
+    mask = cond[:, 3:4].contiguous().to(cuda_dev) if sum_mode else None
+    rows, tab = diff._timestep_rows(n, cuda_dev), diff._coef_table(cuda_dev)
+    eps = torch.empty_like(x)
+    _lib.check(_lib.lib().eo_sample_ddpm(C.c_void_p(m._handle), _lib.ptr(x), _lib.ptr(tape_d), _lib.ptr(gt), _lib.ptr(mask),
+                                         None, 0, None, _lib.ptr(rows), _lib.ptr(tab), _lib.ptr(eps), T, n, 3, size, size,
+                                         int(clip), _lib.stream_ptr()), "eo_sample_ddpm")
+    torch.cuda.synchronize()
+    assert torch.equal(x, want)
