@@ -63,6 +63,7 @@ SIGNATURES = {
     "eo_ddpm_step_mix": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "eo_ddim_step": (_I, [_P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _L, _P]),
     "eo_cfg_combine": (_I, [_P, _P, _F, _P, _L, _P]),
+    "eo_sample_ddim": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "eo_sample_ddpm": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "eo_post_map": (_I, [_P, _P, _L, _I, _F, _P]),
     "eo_post_dim_masked": (_I, [_P, _P, _P, _I, _I, _I, _P]),

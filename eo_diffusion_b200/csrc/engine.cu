@@ -1601,4 +1601,24 @@ int eo_sample_ddpm(eo_unet* u, float* x, const float* noise_tape, const float* g
   return EO_OK;
 }
 
+// DDIMSampler.ddim_sampling's loop (diffusion/ddim.py:114-164) over the per-step entry points
+int eo_sample_ddim(eo_unet* u, float* x, const float* noise_tape, const float* cond, int Cc, const int64_t* y,
+                   const int64_t* timestep_rows, const float* scalars, float* eps_scratch, float* pred_x0, int S, int B, int Cx,
+                   int H, int W, void* stream) {
+  EO_REQUIRE(u && x && timestep_rows && scalars && eps_scratch && pred_x0, EO_ERR_ARG, "eo_sample_ddim: null argument");
+  EO_REQUIRE(S >= 1 && B >= 1 && Cx >= 1 && H >= 1 && W >= 1, EO_ERR_ARG, "eo_sample_ddim: bad extents");
+  const int64_t n = (int64_t)B * Cx * H * W;
+  for (int k = 0; k < S; ++k) {
+    const int index = S - 1 - k;
+    const float* sc = scalars + (size_t)index * 6;
+    EO_REQUIRE(noise_tape || sc[4] == 0.0f, EO_ERR_ARG, "eo_sample_ddim: sigma[%d] != 0 needs a noise tape", index);
+    int rc = eo_unet_forward(u, x, Cx, cond, Cc, timestep_rows + (size_t)index * B, y, eps_scratch, B, stream);
+    if (rc) return rc;
+    rc = eo_ddim_step(x, eps_scratch, noise_tape ? noise_tape + (size_t)k * n : nullptr, x, pred_x0, sc[0], sc[1], sc[2], sc[3],
+                      sc[4], sc[5], n, stream);
+    if (rc) return rc;
+  }
+  return EO_OK;
+}
+
 }  // extern "C"

@@ -210,6 +210,20 @@ EO_API int eo_ddim_step(const float* x, const float* e_t, const float* noise, fl
                  float dir_coef, float sigma_t, float temperature, int64_t n_elems,
                  void* stream);
 
+/* The whole DDIM trajectory in one call: the loop of DDIMSampler.ddim_sampling (diffusion/ddim.py:114-164) over
+ * p_sample_ddim (:166-207), without classifier-free guidance and callbacks.
+ *   x             [B, Cx, H, W]: in x_T, out the final sample
+ *   noise_tape    [S][B, Cx, H, W]: tape[k] = the draw of ddim.py:203 at the k-th iteration (index = S-1-k), or NULL
+ *                 when every sigma is 0 (eta = 0)
+ *   cond, Cc, y   as in eo_unet_forward
+ *   timestep_rows [S][B] int64 device, row `index` = ddim_timesteps[index] repeated
+ *   scalars       HOST array [S][6] of the fp32 values of eo_ddim_step for each index:
+ *                 sqrt_a_t, sqrt_1m_a_t, sqrt_a_prev, dir_coef, sigma_t, temperature
+ *   eps_scratch, pred_x0  [B, Cx, H, W] work buffers (pred_x0 holds the last step's x0 prediction on return) */
+EO_API int eo_sample_ddim(eo_unet* u, float* x, const float* noise_tape, const float* cond, int Cc, const int64_t* y,
+                   const int64_t* timestep_rows, const float* scalars, float* eps_scratch, float* pred_x0,
+                   int S, int B, int Cx, int H, int W, void* stream);
+
 /* Classifier-free guidance combine e = e_u + s*(e_c - e_u) (ddim.py:180-181). */
 EO_API int eo_cfg_combine(const float* e_uncond, const float* e_cond, float scale, float* e_out,
                    int64_t n_elems, void* stream);

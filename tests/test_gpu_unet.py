@@ -281,3 +281,4 @@ def test_whole_loop_entry_point_equals_host_loop(cuda_dev, sum_mode, clip):
                                          int(clip), _lib.stream_ptr()), "eo_sample_ddpm")
     torch.cuda.synchronize()
     assert torch.equal(x, want)
+
