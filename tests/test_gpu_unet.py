@@ -282,3 +282,36 @@ def test_whole_loop_entry_point_equals_host_loop(cuda_dev, sum_mode, clip):
     torch.cuda.synchronize()
     assert torch.equal(x, want)
 
+
+
+@pytest.mark.parametrize("eta", [0.0, 0.5])
+def test_whole_loop_ddim_entry_point_equals_host_loop(cuda_dev, eta):
+    """eo_sample_ddim against DDIMSampler.sample on the same noise tape: bit-identical."""
+    import ctypes as C
+    from eo_diffusion_b200 import _lib
+    from eo_diffusion_b200.ddim import _f32
+    g = golden(f"tiny_ddim_S4_T8_eta{eta}")
+    m, cfg = model_for(g, cuda_dev, "fp32")
+    d = EODiffusion(m, 16, 3, timesteps=8).to(cuda_dev)
+    smp = DDIMSampler(d)
+    n, S = int(g["n"]), 4
+    x_T, tape = O.noise_tape((n, 3, 16, 16), S, seed=int(g["tape_seed"]))
+    with replay(tape, [None] * S):
+        want, inter = smp.sample(S, n, (3, 16, 16), eta=eta, x_T=x_T.to(cuda_dev), verbose=False, log_every_t=1)
+    scal = []
+    for index in range(S):                # the scalars of p_sample_ddim (ddim.py:187-195), same fp32 torch ops
+        a_t, a_prev = _f32(smp.ddim_alphas[index]), _f32(smp.ddim_alphas_prev[index])
+        sigma_t = _f32(smp.ddim_sigmas[index])
+        scal += [float(a_t.sqrt()), float(_f32(smp.ddim_sqrt_one_minus_alphas[index])), float(a_prev.sqrt()),
+                 float((1. - a_prev - sigma_t ** 2).sqrt()), float(sigma_t), 1.0]
+    scal_c = (C.c_float * len(scal))(*scal)
+    rows = torch.stack([torch.full((n,), int(t), dtype=torch.long) for t in smp.ddim_timesteps]).to(cuda_dev).contiguous()
+    x = x_T.clone().to(cuda_dev).contiguous()
+    tape_d = torch.stack(list(tape)).to(cuda_dev).contiguous()
+    eps, px0 = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(_lib.lib().eo_sample_ddim(C.c_void_p(m._handle), _lib.ptr(x), _lib.ptr(tape_d) if eta > 0 else None, None, 0,
+                                         None, _lib.ptr(rows), scal_c, _lib.ptr(eps), _lib.ptr(px0), S, n, 3, 16, 16,
+                                         _lib.stream_ptr()), "eo_sample_ddim")
+    torch.cuda.synchronize()
+    assert torch.equal(x, want)
+    assert torch.equal(px0, inter["pred_x0"][-1])
