@@ -51,6 +51,8 @@ SIGNATURES = {
     "eo_unet_set_weight": (_I, [_P, C.c_char_p, _P, C.POINTER(_L), _I]),
     "eo_unet_finalize": (_I, [_P, _I, _I, _I, _I, _P]),
     "eo_unet_forward": (_I, [_P, _P, _I, _P, _I, _P, _P, _P, _I, _P]),
+    "eo_unet_build_time_tables": (_I, [_P, _I, _P]),
+    "eo_unet_clear_time_tables": (_I, [_P]),
     "eo_unet_forward_timed": (_I, [_P, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P]),
     "eo_unet_num_ops": (_I, [_P]),
     "eo_unet_op_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),

@@ -137,6 +137,16 @@ struct eo_unet {
   float *w_emb_cat = nullptr, *b_emb_cat = nullptr;
   double* gn_sums = nullptr;
   int n_gn = 0;
+  // timestep tables (eo_unet_build_time_tables): row t = the per-step embedding table `tb` of timestep value t,
+  // computed once per sampling loop instead of once per step (unet_openai.py:763, :374-376)
+  float* tt_table = nullptr;
+  int tt_n = 0;
+  void release_time_tables() {
+    if (tt_table) { cudaFree(tt_table); dev_bytes -= (int64_t)tt_n * tb_total * sizeof(float); }
+    tt_table = nullptr; tt_n = 0;
+    release_graphs_only();          // captured graphs contain the other variant of the time_embed op
+  }
+  int build_time_tables(int n, cudaStream_t st);
   double* ch_stats = nullptr;       // per-channel GroupNorm sums emitted by conv epilogues (zeroed per forward)
   size_t ch_stats_floats = 0;       // element count
   // per-forward io (read by ops at launch time)
@@ -144,7 +154,7 @@ struct eo_unet {
   const float* io_cond = nullptr; int io_cc = 0;
   const int64_t* io_t = nullptr; const int64_t* io_y = nullptr;
   float* io_out = nullptr;
-  // CUDA-graph replay of the forward (EO_GRAPH=0 disables): decisive for launch-bound sizes (64x64 batch 1:
+  // CUDA-graph replay of the forward: decisive for launch-bound sizes (64x64 batch 1:
   // 2.69 -> 2.35 ms per step), and still 0.9 ms of a 69.6 ms step at 256x256 batch 64 (171 launch gaps).  The graph
   // reads its inputs from / writes its output to engine-owned staging buffers, so one instantiation serves every
   // step of a sampling loop; key = (B, Cx, Cc, has y).
@@ -153,9 +163,12 @@ struct eo_unet {
   cudaStream_t graph_stream = nullptr;          // capture stream (the caller's may be the legacy default stream)
   float *gs_x = nullptr, *gs_cond = nullptr, *gs_out = nullptr;
   int64_t *gs_t = nullptr, *gs_y = nullptr;
-  void release_graphs() {
+  void release_graphs_only() {
     for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     graphs.clear();
+  }
+  void release_graphs() {
+    release_graphs_only();
     if (graph_stream) { cudaStreamDestroy(graph_stream); graph_stream = nullptr; }
     gs_x = gs_cond = gs_out = nullptr; gs_t = gs_y = nullptr;   // freed with `owned`
   }
@@ -166,6 +179,7 @@ struct eo_unet {
   ~eo_unet() { release_plan(); }
 
   void release_plan() {
+    release_time_tables();
     release_graphs();
     for (auto* p : tc_plans) tc_conv_plan_destroy(p);
     for (auto* p : attn_plans) tc_attn_plan_destroy(p);
@@ -462,6 +476,7 @@ struct eo_unet {
   // bf16 tensor-core conv.  `tsegs` carry activation + taps; weights in `segs` (same order).
   struct TcSegSpec {
     Act act; int batch_mult = 1; int ntaps = 9; int8_t dh[9]; int8_t dw[9]; int plane[9];
+    int stride = 1;   // 2: the source grid is twice the output grid (stride-2 conv read through a strided tensor map)
     bool has_gn = false; GnOut gn{}; int gn_coff = 0; int silu = 0;   // GroupNorm (+SiLU) folded into the operand load
   };
   static TcSegSpec with_gn(TcSegSpec s, const GnOut& g, int coff, int silu) {
@@ -470,9 +485,7 @@ struct eo_unet {
   }
   // GroupNorm + SiLU can ride on the conv's operand load (persistent kernel; 3x3 windows need halo patches)
   bool can_fuse_gn(int ksize, int Ho, int Wo, int C) const {
-    static int on = -1;
-    if (on < 0) { const char* e = std::getenv("EO_GN_FUSE"); on = (e && e[0] == '0') ? 0 : 1; }
-    if (!on || !tc_conv3_enabled() || C % 64 != 0) return false;
+    if (C % 64 != 0) return false;
     // a 1x1 conv would redo the transform for each of its N tiles (qkv: 6x) against one K block of MMA work
     return ksize == 3 && tc_conv_patch_supported(Ho, Wo);
   }
@@ -487,7 +500,7 @@ struct eo_unet {
   }
   // a plain 3x3 window over one tensor: served from halo patches when the output grid allows it
   static bool patchable(const TcSegSpec& s, int Ho, int Wo) {
-    if (s.ntaps != 9 || !tc_conv_patch_supported(Ho, Wo)) return false;
+    if (s.ntaps != 9 || s.stride != 1 || !tc_conv_patch_supported(Ho, Wo)) return false;
     for (int t = 0; t < 9; ++t)
       if (s.dh[t] != t / 3 - 1 || s.dw[t] != t % 3 - 1 || s.plane[t] != 0) return false;
     return true;
@@ -509,7 +522,7 @@ struct eo_unet {
   int plan_conv_tc(const std::string& name, const std::vector<TcSegSpec>& tsegs, const std::vector<PackSeg>& segs_in,
                    int Cout_rows, const int* d_row_map, const float* bias_a, const float* bias_b, int tb_off,
                    const Act* residual, int Ho, int Wo, Act* out, cudaStream_t st, bool want_stats = true,
-                   const OutView* view = nullptr, double alg_flops = -1.0) {
+                   const OutView* view = nullptr, double alg_flops = -1.0, int nchw_C = 0) {
     std::vector<bool> patch;
     for (auto& ts : tsegs) patch.push_back(patchable(ts, Ho, Wo) && ts.act.C % 64 == 0);
     const std::vector<PackSeg> segs = patch_order(segs_in, patch);
@@ -519,7 +532,8 @@ struct eo_unet {
     float* bias = nullptr;
     if (bias_a || bias_b) { rc = pack_bias2(bias_a, bias_b, Cout_rows, d_row_map, &bias, st); if (rc) return rc; }
     last_packed_bias = bias;
-    Act o = view ? view->target : new_act(Cout_rows, Ho, Wo);
+    // nchw_C > 0: the head -- fp32 NCHW straight to the caller's eps buffer (io_out at launch), no activation
+    Act o = view ? view->target : (nchw_C ? Act() : new_act(Cout_rows, Ho, Wo));
     if (!view && want_stats && tc_conv_stats_supported(Ho, Wo)) {
       o.stats = (long long)ch_stats_floats;
       ch_stats_floats += (size_t)Bmax * Cout_rows * 2;
@@ -537,6 +551,7 @@ struct eo_unet {
       for (int i = 0; i < p.nseg; ++i) {
         p.seg[i].ptr = ptr(tv[i].act.off); p.seg[i].C = tv[i].act.C;
         p.seg[i].Bt = Bmax * tv[i].batch_mult; p.seg[i].ntaps = tv[i].ntaps; p.seg[i].patch = patch[i] ? 1 : 0;
+        p.seg[i].stride = tv[i].stride;
         if (tv[i].has_gn) {
           p.seg[i].gn_scale = ptr<float>(tv[i].gn.scale_off); p.seg[i].gn_shift = ptr<float>(tv[i].gn.shift_off);
           p.seg[i].gn_ld = tv[i].gn.C; p.seg[i].gn_coff = tv[i].gn_coff; p.seg[i].silu = tv[i].silu;
@@ -548,7 +563,8 @@ struct eo_unet {
       p.B = Bmax; p.H = Ho; p.W = Wo; p.Wp = Wp; p.Ktot = K; p.Cout = Cout_rows; p.bias = bias;
       if (tb_off >= 0) { p.bias_nc = tb + tb_off; p.ld_bias_nc = tb_total; }
       p.residual = has_res ? ptr(res.off) : nullptr;
-      p.out = ptr(o.off);
+      p.out = nchw_C ? nullptr : ptr(o.off);
+      p.out_nchw_C = nchw_C;
       if (has_view) {
         p.out = ptr<__nv_bfloat16>(o.off) + vw.off;
         p.out_sw = vw.sw; p.out_sh = vw.sh; p.out_sn = vw.sn;
@@ -556,8 +572,9 @@ struct eo_unet {
       p.stats = o.stats >= 0 ? ch_stats + o.stats : nullptr;
       return tc_conv_plan_create(p, &tc_plans[plan_idx]);
     };
-    push(name, [=](int B, cudaStream_t stx) -> int { return tc_conv_launch(tc_plans[plan_idx], B, stx); }, 1, prepare);
-    note(tc_conv3_enabled() ? "k_conv_tc3" : "k_conv_tc",
+    push(name, [=](int B, cudaStream_t stx) -> int { return tc_conv_launch(tc_plans[plan_idx], B, stx, nchw_C ? io_out : nullptr); },
+         1, prepare);
+    note("k_conv_tc3",
          has_view ? vw.alg_flops : alg_flops >= 0 ? alg_flops : 2.0 * Ho * Wo * Cout_rows * K, 0);
     *out = o;
     return EO_OK;
@@ -782,7 +799,7 @@ struct eo_unet {
       push(p + "attention", [=](int B, cudaStream_t stx) -> int {
         return launch_attention_simt(ptr<float>(qkv.off), ptr<float>(a.off), B, T, heads, ch, 3 * C, hs, ps, stx);
       });
-      note("k_attention_simt", 4.0 * heads * (double)T * T * ch, 0);
+      note(ch > 64 ? "k_attention_wide" : "k_attention_simt", 4.0 * heads * (double)T * T * ch, 0);
       free_act(qkv);
       SrcSpec sa; sa.act = a; sa.ksize = 1;
       rc = plan_conv_fp32(p + "proj_out", {sa}, {{wp, C, 1, 0, C}}, C, w(p + "proj_out.bias"), nullptr, -1, &x, 1, 0, out, st);
@@ -790,8 +807,28 @@ struct eo_unet {
       free_act(a);
     } else {
       if (ch > 64 || ch % 8 != 0) {
-        set_error("attention %s: head dimension %d unsupported in bf16 mode (multiple of 8, <= 64)", p.c_str(), ch);
-        return EO_ERR_ARG;
+        // head dimensions the tensor-core kernel does not take (the reference's own scripts use num_heads = 1:
+        // 512 / 1024 channels per head, train.py:50, inference.py:59): qkv in the reference's channel order from
+        // the tensor-core 1x1 conv, attention by the one-warp-per-query kernel in fp32 arithmetic
+        Act xn = plan_gn_apply(p + "norm", x, nullptr, g, 0);
+        free_gn(g);
+        Act qkv;
+        rc = plan_conv_tc(p + "qkv", {seg1x1(xn)}, {{wq, C, 1, 0, C}}, 3 * C, nullptr, w(p + "qkv.bias"), nullptr, -1, nullptr,
+                          x.H, x.W, &qkv, st, /*want_stats=*/false);
+        if (rc) return rc;
+        free_act(xn);
+        Act a = new_act(C, x.H, x.W);
+        const int hs = new_order ? ch : 3 * ch, ps = new_order ? C : ch;
+        push(p + "attention", [=](int B, cudaStream_t stx) -> int {
+          return launch_attention_wide(ptr(qkv.off), ptr(a.off), DT_BF16, B, T, heads, ch, 3 * C, hs, ps, stx);
+        });
+        note("k_attention_wide", 4.0 * heads * (double)T * T * ch, 0);
+        free_act(qkv);
+        rc = plan_conv_tc(p + "proj_out", {seg1x1(a)}, {{wp, C, 1, 0, C}}, C, nullptr, w(p + "proj_out.bias"), nullptr, -1, &x,
+                          x.H, x.W, out, st);
+        if (rc) return rc;
+        free_act(a);
+        return EO_OK;
       }
       const bool fuse = can_fuse_gn(1, x.H, x.W, C);
       Act xn;
@@ -852,27 +889,13 @@ struct eo_unet {
       SrcSpec s; s.act = x; s.ksize = 3;
       return plan_conv_fp32(L.prefix + "op", {s}, {{wd, L.cin, 3, 0, L.cin}}, L.cout, w(p + "bias"), nullptr, -1, nullptr, 2, 0, out, st);
     }
-    // four parity planes [(hp,wp)][B][H/2][W/2][C]; tap (kh,kw) reads plane ((kh+1)&1,(kw+1)&1)
-    // shifted by (kh==0 ? -1 : 0, kw==0 ? -1 : 0)
-    Act planes = new_act(x.C, x.H / 2, x.W / 2, 4);
-    Act xx = x;
-    const int bstride = Bmax;   // plane pitch in images: the tensor map is encoded for Bmax
-    push(L.prefix + "op.s2d", [=](int B, cudaStream_t stx) -> int {
-      return launch_space_to_depth(ptr(xx.off), ptr(planes.off), B, bstride, xx.H, xx.W, xx.C, stx);
-    });
-    note("k_space_to_depth", 0, 2.0 * x.H * x.W * x.C * 2);
-    TcSegSpec s; s.act = planes; s.act.H = x.H / 2; s.act.W = x.W / 2; s.batch_mult = 4; s.ntaps = 9;
-    for (int t = 0; t < 9; ++t) {
-      int kh = t / 3, kw = t % 3;
-      int hp = (kh + 1) & 1, wp = (kw + 1) & 1;
-      s.dh[t] = (int8_t)(kh == 0 ? -1 : 0); s.dw[t] = (int8_t)(kw == 0 ? -1 : 0);
-      s.plane[t] = hp * 2 + wp;
-    }
-    int rc = plan_conv_tc(L.prefix + "op", {s}, {{wd, L.cin, 3, 0, L.cin}}, L.cout, nullptr, w(p + "bias"), nullptr, -1, nullptr,
-                          x.H / 2, x.W / 2, out, st);
-    if (rc) return rc;
-    free_act(planes);
-    return EO_OK;
+    // output pixel (h, w) reads source pixels (2h + kh - 1, 2w + kw - 1): nine taps fetched straight from the
+    // full-resolution tensor by a tensor map with traversal stride 2 (out-of-image rows / columns zero-filled by the
+    // TMA unit = the conv's padding) -- no space-to-depth copy of the input
+    TcSegSpec s = seg3x3(x);
+    s.stride = 2;
+    return plan_conv_tc(L.prefix + "op", {s}, {{wd, L.cin, 3, 0, L.cin}}, L.cout, nullptr, w(p + "bias"), nullptr, -1, nullptr,
+                        x.H / 2, x.W / 2, out, st);
   }
 
   // Upsample.forward (unet_openai.py:229-242): nearest x2 then conv 3x3
@@ -884,9 +907,7 @@ struct eo_unet {
       SrcSpec s; s.act = x; s.ksize = 3;
       return plan_conv_fp32(L.prefix + "conv", {s}, {{wu, L.cin, 3, 0, L.cin}}, L.cout, w(p + "bias"), nullptr, -1, nullptr, 1, 1, out, st);
     }
-    static int subpix = -1;
-    if (subpix < 0) { const char* e = std::getenv("EO_UP_SUBPIXEL"); subpix = (e && e[0] == '0') ? 0 : 1; }
-    if (subpix && tc_conv3_enabled() && tc_conv_stats_supported(x.H, x.W)) {
+    if (tc_conv_stats_supported(x.H, x.W)) {
       // Four sub-pixel convolutions over the low-resolution input, one per output parity (a, b), with the
       // 3x3 taps that read the same source pixel summed (k_fold_upsample_weight): 4/9 of the FLOPs and no
       // materialised upsampled tensor.  Each writes its quarter of the output through a strided view.
@@ -985,13 +1006,17 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
                "bf16 mode needs model_channels %% 64 == 0 (got %d)", cfg.model_channels);
   mode = mode_; Bmax = Bmax_; H = H_; W = W_;
   act_dt = mode == EO_MODE_FP32 ? DT_F32 : DT_BF16;
+#ifdef EO_DEVTOOLS
   arena.keep = std::getenv("EO_DEBUG_KEEP") != nullptr;
+#endif
   int rc;
   // private copies of every parameter the kernels read directly at run time (GroupNorm affine,
   // biases, Linear / embedding matrices); convolution weights are only read by the packers below
   for (auto& ws : wspecs) {
     ws.priv = nullptr;
-    if (ws.shape.size() > 2) continue;
+    // (the stem weight too: its (x, cond) split is packed at the first forward that uses it, when the caller's
+    // staging copy may be gone)
+    if (ws.shape.size() > 2 && ws.name != in_blocks[0].layers[0].prefix + "weight") continue;
     size_t n = 1;
     for (int64_t d : ws.shape) n *= (size_t)d;
     float* p = nullptr;
@@ -1032,6 +1057,9 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
     const float *w2 = w("time_embed.2.weight"), *b2 = w("time_embed.2.bias");
     const float* lab = cfg.num_classes > 0 ? w("label_emb.weight") : nullptr;
     push("time_embed", [=](int B, cudaStream_t s) -> int {
+      // a precomputed table serves every forward without class labels (label_emb(y) is added BEFORE the
+      // projections, :764-766, so those rows depend on (t, y))
+      if (tt_table && !io_y) return launch_gather_rows(tt_table, tt_n, tb_total, io_t, B, tb, s);
       int r = launch_sinusoid(io_t, freqs, B, mc / 2, e0, s);
       if (r) return r;
       if ((r = launch_linear(e0, w0, b0, nullptr, nullptr, nullptr, 0, B, mc, ted, l1, s))) return r;
@@ -1043,10 +1071,8 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
 
   // ---- stem: conv3x3 over cat(x, cond), NCHW fp32 -> NHWC (unet_openai.py:754-756, :608)
   Act h;
-  static int tc_ends = -1;      // EO_TC_ENDS=0: the SIMT stem and head (A/B switch)
-  if (tc_ends < 0) { const char* e = std::getenv("EO_TC_ENDS"); tc_ends = (e && e[0] == '0') ? 0 : 1; }
   const Layer& L0 = in_blocks[0].layers[0];
-  if (mode == EO_MODE_BF16 && tc_ends && tc_conv3_enabled() && 18 * L0.cin <= 64 && L0.cout % 64 == 0) {
+  if (mode == EO_MODE_BF16 && 18 * L0.cin <= 64 && L0.cout % 64 == 0) {
     // few input channels: the 3x3 windows (bf16 value + rounding residual of every element, exact to 2^-17)
     // become one 64-channel pixel, and the stem a 64-deep 1x1 convolution on the tensor cores, GroupNorm
     // statistics of its output included
@@ -1064,7 +1090,7 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
                            -1, nullptr, H, W, &h, st, true, nullptr, 2.0 * H * W * L0.cout * 9 * cin)))
       return rc;
     free_act(col);
-  } else if (mode == EO_MODE_BF16 && tc_ends && tc_conv3_enabled() && 2 * L0.cin <= 64 && L0.cout % 64 == 0) {
+  } else if (mode == EO_MODE_BF16 && 2 * L0.cin <= 64 && L0.cout % 64 == 0) {
     // up to 32 input channels (the multispectral concat configuration: 13 + 15): the input becomes one 64-channel
     // bf16 NHWC block (values + rounding residuals) and the stem an ordinary 3x3 tensor-core convolution
     Act xin = new_act(64, H, W);
@@ -1150,9 +1176,9 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
     h = o; named[out_blocks[i].name] = h;
   }
   // ---- head: conv3x3(SiLU(GN(h))) -> NCHW fp32 (unet_openai.py:739-743, :780)
-  if (mode == EO_MODE_BF16 && tc_ends && cfg.out_channels <= 64 && can_fuse_gn(3, H, W, final_ch)) {
+  if (mode == EO_MODE_BF16 && cfg.out_channels <= 64 && can_fuse_gn(3, H, W, final_ch)) {
     // on the tensor cores with the output channels padded to one 64-wide tile (zero weight rows) and
-    // GroupNorm + SiLU folded into the operand load; a layout pass extracts the real channels
+    // GroupNorm + SiLU folded into the operand load; the epilogue writes the real channels as fp32 NCHW
     GnOut g = plan_gn("out.0", h, nullptr, w("out.0.weight"), w("out.0.bias"));
     const int cout = cfg.out_channels, C = final_ch;
     std::vector<int> rmap(64, -1);
@@ -1161,13 +1187,11 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
     if ((rc = dmalloc(&d_rmap, (size_t)64))) return rc;
     EO_CHECK_CUDA(cudaMemcpyAsync(d_rmap, rmap.data(), 64 * sizeof(int), cudaMemcpyHostToDevice, st));
     EO_CHECK_CUDA(cudaStreamSynchronize(st));   // rmap is a stack-lifetime host buffer
-    Act o64;
+    Act none;
     if ((rc = plan_conv_tc("out", {with_gn(seg3x3(h), g, 0, 1)}, {{w("out.2.weight"), C, 3, 0, C}}, 64, d_rmap, w("out.2.bias"),
-                           nullptr, -1, nullptr, H, W, &o64, st, false, nullptr, 2.0 * H * W * cout * 9 * C)))
+                           nullptr, -1, nullptr, H, W, &none, st, false, nullptr, 2.0 * H * W * cout * 9 * C, cout)))
       return rc;
     free_gn(g);
-    push("out.nchw", [=](int B, cudaStream_t s) -> int { return launch_head_to_nchw(ptr(o64.off), 64, io_out, B, H * W, cout, s); });
-    note("k_head_to_nchw", 0, (double)H * W * (32 + cout * 4));
   } else {
     GnOut g = plan_gn("out.0", h, nullptr, w("out.0.weight"), w("out.0.bias"));
     float* Wp = nullptr; int K = 0;
@@ -1212,6 +1236,43 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
   EO_CHECK_CUDA(cudaStreamSynchronize(st));   // weight packing done before callers may free sources
   finalized = true;
   return EO_OK;
+}
+
+// The embedding path of `n` timestep values 0 .. n-1 with the SAME kernels the per-step path uses (k_linear
+// reduces each output element on its own, so a row does not depend on what else is in the batch: table rows are
+// bit-identical to the rows the per-step path would produce).
+int eo_unet::build_time_tables(int n, cudaStream_t st) {
+  EO_REQUIRE(finalized, EO_ERR_STATE, "eo_unet_build_time_tables before eo_unet_finalize");
+  EO_REQUIRE(n >= 1 && n <= (1 << 20), EO_ERR_ARG, "eo_unet_build_time_tables: %d timesteps", n);
+  EO_REQUIRE(tb_total % 4 == 0, EO_ERR_ARG, "eo_unet_build_time_tables: table width %d", tb_total);
+  if (tt_table && tt_n >= n) return EO_OK;
+  release_time_tables();
+  const int mc = cfg.model_channels;
+  float *t_e0 = nullptr, *t_l1 = nullptr, *t_emb = nullptr;
+  int64_t* t_idx = nullptr;
+  auto cleanup = [&]() { cudaFree(t_e0); cudaFree(t_l1); cudaFree(t_emb); cudaFree(t_idx); };
+  cudaError_t e = cudaMalloc(&tt_table, (size_t)n * tb_total * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&t_e0, (size_t)n * mc * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&t_l1, (size_t)n * ted * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&t_emb, (size_t)n * ted * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&t_idx, (size_t)n * sizeof(int64_t));
+  if (e != cudaSuccess) {
+    cleanup(); cudaFree(tt_table); tt_table = nullptr;
+    set_error("eo_unet_build_time_tables: %s", cudaGetErrorString(e));
+    return EO_ERR_CUDA;
+  }
+  tt_n = n;
+  dev_bytes += (int64_t)n * tb_total * sizeof(float);
+  int rc = launch_iota64(t_idx, n, st);
+  if (!rc) rc = launch_sinusoid(t_idx, w("time_embed.freqs"), n, mc / 2, t_e0, st);
+  if (!rc) rc = launch_linear(t_e0, w("time_embed.0.weight"), w("time_embed.0.bias"), nullptr, nullptr, nullptr, 0, n, mc, ted, t_l1, st);
+  if (!rc) rc = launch_linear(t_l1, w("time_embed.2.weight"), w("time_embed.2.bias"), nullptr, nullptr, nullptr, 1, n, ted, ted, t_emb, st);
+  if (!rc) rc = launch_linear(t_emb, w_emb_cat, b_emb_cat, nullptr, nullptr, nullptr, 1, n, ted, tb_total, tt_table, st);
+  e = cudaStreamSynchronize(st);          // the scratch buffers die here
+  cleanup();
+  if (!rc && e != cudaSuccess) { set_error("eo_unet_build_time_tables: %s", cudaGetErrorString(e)); rc = EO_ERR_CUDA; }
+  if (rc) release_time_tables();
+  return rc;
 }
 
 int eo_unet::forward(const float* x, int Cx, const float* cond, int Cc, const int64_t* t, const int64_t* y,
@@ -1277,11 +1338,8 @@ int eo_unet::run_ops(int B, cudaStream_t st) {
 // over staging buffers, later ones are four small copies + one graph launch.  *handled = false: run eagerly.
 int eo_unet::forward_graph(const float* x, int Cx, const float* cond, int Cc, const int64_t* t, const int64_t* y,
                            float* out, int B, cudaStream_t st, bool* handled) {
-  static int graph_mode = -2;
-  if (graph_mode == -2) { const char* e = std::getenv("EO_GRAPH"); graph_mode = e ? atoi(e) : -1; }
   *handled = false;
-  if (graph_mode == 0) return EO_OK;
-  const long long key = (((long long)B * 64 + Cx) * 64 + Cc) * 2 + (y ? 1 : 0);
+  const long long key = ((((long long)B * 64 + Cx) * 64 + Cc) * 2 + (y ? 1 : 0)) * 2 + (tt_table ? 1 : 0);
   GraphSlot& g = graphs[key];
   if (g.failed || ++g.seen == 1) return EO_OK;
   const size_t hw = (size_t)H * W;
@@ -1452,13 +1510,26 @@ int eo_unet_op_info(const eo_unet* u, int index, const char** name, const char**
 }
 
 int64_t eo_unet_device_bytes(const eo_unet* u) { return u ? u->dev_bytes : 0; }
-int eo_unet_launches_per_forward(const eo_unet* u) { return u ? u->n_launches + 2 : 0; }   // + the two GN memsets
+// + the two GN memsets; with timestep tables installed the embedding path is one gather instead of four launches
+int eo_unet_launches_per_forward(const eo_unet* u) { return u ? u->n_launches + 2 - (u->tt_table ? 3 : 0) : 0; }
+
+int eo_unet_build_time_tables(eo_unet* u, int n_timesteps, void* stream) {
+  EO_REQUIRE(u, EO_ERR_ARG, "eo_unet_build_time_tables: null handle");
+  return u->build_time_tables(n_timesteps, (cudaStream_t)stream);
+}
+
+int eo_unet_clear_time_tables(eo_unet* u) {
+  EO_REQUIRE(u, EO_ERR_ARG, "eo_unet_clear_time_tables: null handle");
+  u->release_time_tables();
+  return EO_OK;
+}
 
 int64_t eo_unet_read_activation(eo_unet* u, const char* name, float* out_dev, int64_t capacity, int B, void* stream) {
   EO_REQUIRE(u && name && out_dev, EO_ERR_ARG, "eo_unet_read_activation: null argument");
   EO_REQUIRE(u->finalized, EO_ERR_STATE, "eo_unet_read_activation before finalize");
   EO_REQUIRE(u->arena.keep, EO_ERR_STATE,
-             "eo_unet_read_activation needs EO_DEBUG_KEEP=1 at finalize (workspace reuse overwrites activations otherwise)");
+             "eo_unet_read_activation needs a -DEO_DEVTOOLS build and EO_DEBUG_KEEP=1 at finalize (workspace reuse "
+             "overwrites activations otherwise)");
   auto it = u->named.find(name);
   EO_REQUIRE(it != u->named.end(), EO_ERR_KEY, "eo_unet_read_activation: unknown activation '%s'", name);
   const Act& a = it->second;
@@ -1500,8 +1571,9 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
     p.seg[0].patch = patch ? 1 : 0;
     // development aid (tools/conv_check.py): EO_TEST_GN=1 folds an identity GroupNorm affine (scale 1,
     // shift 0) into the operand load, =2 adds the SiLU (the caller then compares against conv(silu(x)))
+#ifdef EO_DEVTOOLS
     const char* tg = std::getenv("EO_TEST_GN");
-    if (tg && (tg[0] == '1' || tg[0] == '2') && tc_conv3_enabled() && patch) {
+    if (tg && (tg[0] == '1' || tg[0] == '2') && patch) {
       std::vector<float> ones((size_t)B * Cin, 1.0f);
       EO_CHECK_CUDA(cudaMalloc(&gn_buf, 2 * ones.size() * sizeof(float)));
       EO_CHECK_CUDA(cudaMemsetAsync(gn_buf, 0, 2 * ones.size() * sizeof(float), st));
@@ -1510,15 +1582,18 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
       p.seg[0].gn_scale = gn_buf; p.seg[0].gn_shift = gn_buf + ones.size(); p.seg[0].gn_ld = Cin;
       p.seg[0].silu = tg[0] == '2';
     }
+#endif
     p.B = B; p.H = H; p.W = W; p.Wp = Wp; p.Ktot = K; p.Cout = Cout; p.bias = bias;
     p.residual = residual; p.out = y_bf16;
     // development aid (tools/conv3_trace.py): EO_TEST_STATS=1 also emits the fused GroupNorm statistics
+#ifdef EO_DEVTOOLS
     const char* tsx = std::getenv("EO_TEST_STATS");
     if (tsx && tsx[0] == '1' && tc_conv_stats_supported(H, W)) {
       EO_CHECK_CUDA(cudaMalloc(&stats_buf, (size_t)B * Cout * 2 * sizeof(double)));
       EO_CHECK_CUDA(cudaMemsetAsync(stats_buf, 0, (size_t)B * Cout * 2 * sizeof(double), st));
       p.stats = stats_buf;
     }
+#endif
     rc = tc_conv_plan_create(p, &plan);
   }
   if (!rc) rc = tc_conv_launch(plan, B, st);
@@ -1540,8 +1615,13 @@ int eo_debug_conv_trace(void* dev_buf, int n_ctas) {
 int eo_test_attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int heads, int ch, void* stream) {
   int rc = eo_device_check();
   if (rc) return rc;
-  EO_REQUIRE(ch <= 64 && ch % 8 == 0, EO_ERR_ARG, "eo_test_attention_tc: head dimension");
   cudaStream_t st = (cudaStream_t)stream;
+  if (ch > 64 || ch % 8 != 0) {      // the engine's route for wide / odd heads: one warp per query, fp32 arithmetic
+    rc = launch_attention_wide(qkv_bf16, out_bf16, DT_BF16, B, T, heads, ch, heads * 3 * ch, 3 * ch, ch, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) { set_error("eo_test_attention_tc: %s", cudaGetErrorString(e)); rc = EO_ERR_CUDA; }
+    return rc;
+  }
   // re-pack [B,T,heads*3*ch] (legacy order) into the kernel's [B,T,heads*3*64] padded layout
   const int ld_in = heads * 3 * ch, ld = heads * 3 * 64;
   __nv_bfloat16* padded = nullptr;
@@ -1580,10 +1660,16 @@ int eo_sample_ddpm(eo_unet* u, float* x, const float* noise_tape, const float* g
                    int T, int B, int Cx, int H, int W, int clip, void* stream) {
   EO_REQUIRE(u && x && noise_tape && timestep_rows && table && eps_scratch, EO_ERR_ARG, "eo_sample_ddpm: null argument");
   EO_REQUIRE(T >= 1 && B >= 1 && Cx >= 1 && H >= 1 && W >= 1, EO_ERR_ARG, "eo_sample_ddpm: bad extents");
+  EO_REQUIRE(u->finalized, EO_ERR_STATE, "eo_sample_ddpm before eo_unet_finalize");
+  EO_REQUIRE(H == u->H && W == u->W && B <= u->Bmax && Cx == u->cfg.out_channels, EO_ERR_ARG,
+             "eo_sample_ddpm: [%d, %d, %d, %d] does not match the finalized geometry (batch <= %d, %d channels, %d x %d)", B, Cx,
+             H, W, u->Bmax, u->cfg.out_channels, u->H, u->W);
   EO_REQUIRE((gt == nullptr) == (mask == nullptr), EO_ERR_ARG, "eo_sample_ddpm: 'sum' conditioning needs gt and mask");
   const int HW = H * W;
   const size_t n = (size_t)B * Cx * HW;
   int rc;
+  // the loop visits the timestep values T-1 .. 0: their embedding rows are computed once, not once per step
+  if (!y && (rc = u->build_time_tables(T, (cudaStream_t)stream))) return rc;
   if (gt && (rc = eo_ddpm_sum_mix(x, gt, mask, noise_tape, timestep_rows + (size_t)(T - 1) * B, table, x, B, Cx, HW, stream)))
     return rc;
   for (int i = T - 1; i >= 0; --i) {
@@ -1607,6 +1693,10 @@ int eo_sample_ddim(eo_unet* u, float* x, const float* noise_tape, const float* c
                    int H, int W, void* stream) {
   EO_REQUIRE(u && x && timestep_rows && scalars && eps_scratch && pred_x0, EO_ERR_ARG, "eo_sample_ddim: null argument");
   EO_REQUIRE(S >= 1 && B >= 1 && Cx >= 1 && H >= 1 && W >= 1, EO_ERR_ARG, "eo_sample_ddim: bad extents");
+  EO_REQUIRE(u->finalized, EO_ERR_STATE, "eo_sample_ddim before eo_unet_finalize");
+  EO_REQUIRE(H == u->H && W == u->W && B <= u->Bmax && Cx == u->cfg.out_channels, EO_ERR_ARG,
+             "eo_sample_ddim: [%d, %d, %d, %d] does not match the finalized geometry (batch <= %d, %d channels, %d x %d)", B, Cx,
+             H, W, u->Bmax, u->cfg.out_channels, u->H, u->W);
   const int64_t n = (int64_t)B * Cx * H * W;
   for (int k = 0; k < S; ++k) {
     const int index = S - 1 - k;

@@ -93,12 +93,21 @@ int launch_linear(const float* in, const float* W, const float* bias, const floa
                   const float* emb_rows, const int64_t* idx, int silu_in, int B, int K, int N,
                   float* out, cudaStream_t st);
 
+// out[b, :] = table[t[b], :] (rows of ld floats, ld % 4 == 0); NaN rows for t[b] outside [0, n)
+int launch_gather_rows(const float* table, int n, int ld, const int64_t* t, int B, float* out, cudaStream_t st);
+// out[i] = i
+int launch_iota64(int64_t* out, int n, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------
 // attention, fp32 SIMT (parity mode).  qkv is [B,T,ld] with q/k/v of head h at channel
 // offsets h*head_stride + {0,1,2}*part_stride.  out is [B,T,heads*ch].
 // ---------------------------------------------------------------------------------------
 int launch_attention_simt(const float* qkv, float* out, int B, int T, int heads, int ch,
                           int ld, int head_stride, int part_stride, cudaStream_t st);
+// head dimension 65 .. 1024 (the reference's own scripts: num_heads = 1), qkv / out of dtype dt (same layout
+// arguments): one warp per query row, fp32 arithmetic.  launch_attention_simt forwards to it for ch > 64.
+int launch_attention_wide(const void* qkv, void* out, int dt, int B, int T, int heads, int ch, int ld,
+                          int head_stride, int part_stride, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------
 // layout pre-passes of the bf16 mode (bandwidth kernels, 16-byte vectors)
@@ -163,6 +172,9 @@ struct TcConvSeg {
   int gn_ld = 0, gn_coff = 0, silu = 0;
   int patch = 0;              // a plain 3x3 window served from one halo patch per 64 channels; the
                               // segment's weights are then K-ordered (64-channel block, tap, channel)
+  int stride = 1;             // 2: the segment's grid is [Bt, 2H, 2W, C] and output pixel (h, w) reads source pixel
+                              // (2h + dh, 2w + dw): a stride-2 convolution straight from the full-resolution tensor
+                              // (tensor map with traversal stride 2), no space-to-depth copy
 };
 struct TcConvParams {
   TcConvSeg seg[3];
@@ -180,20 +192,22 @@ struct TcConvParams {
   // persistent kernel only: `out` as a strided view (elements) -- pixel (n, h, w) at out + out_sn*n + out_sh*h +
   // out_sw*w; 0 = dense NHWC.  Used by the sub-pixel convolutions of Upsample.
   long long out_sw = 0, out_sh = 0, out_sn = 0;
+  // head convolution (out_nchw_C > 0): channels [0, out_nchw_C) of the accumulator (+ bias) go as fp32 NCHW
+  // [B, out_nchw_C, H, W] to the pointer given at launch (tc_conv_launch's out_nchw) and nothing to `out`, which
+  // may be null: no bf16 rounding of the network output, no layout pass.  Cout must be one 64-wide tile.
+  int out_nchw_C = 0;
   double* stats = nullptr;          // [B, Cout, 2] per-channel (sum, sum of squares) of `out`,
                                     // accumulated with atomics (zeroed by the caller), or null
 };
 // fused statistics need a warp's 32 output rows inside one image
 bool tc_conv_stats_supported(int H, int W);
-// halo patches are available for this output grid (persistent kernel, H % 16 == 0, W % 8 == 0)
+// halo patches are available for this output grid (H % 16 == 0, W % 8 == 0)
 bool tc_conv_patch_supported(int H, int W);
-// the persistent kernel (tc_conv3.cu) is in use (EO_CONV_V2=1 selects the one-tile-per-CTA kernel instead)
-bool tc_conv3_enabled();
 // A prepared launch (tensor maps encoded once at plan time)
 struct TcConvPlan;
 int tc_conv_plan_create(const TcConvParams& p, TcConvPlan** out);
 void tc_conv_plan_destroy(TcConvPlan* p);
-int tc_conv_launch(const TcConvPlan* plan, int B, cudaStream_t st);
+int tc_conv_launch(const TcConvPlan* plan, int B, cudaStream_t st, float* out_nchw = nullptr);
 // development aid: per-CTA phase stamps of subsequent launches ([n_ctas][8] int64, device), null = off
 void tc_conv_set_trace(long long* dev_buf, int n_ctas);
 

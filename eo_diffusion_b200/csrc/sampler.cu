@@ -78,10 +78,10 @@ struct Pack<1> {
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
-k_sum_mix(const float* __restrict__ x_t, const float* __restrict__ gt,
+k_sum_mix(const float* x_t, const float* __restrict__ gt,          // x_t and x_out may alias (eo_b200.h): no __restrict__
           const float* __restrict__ mask, const float* __restrict__ noise,
           const long long* __restrict__ ts, const float* __restrict__ table,
-          float* __restrict__ x_out, int C, int HWv, long long total) {
+          float* x_out, int C, int HWv, long long total) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long plane = i / HWv;
@@ -101,11 +101,11 @@ k_sum_mix(const float* __restrict__ x_t, const float* __restrict__ gt,
 
 template <int VEC, bool CLIP, bool MIX>
 __global__ void __launch_bounds__(256)
-k_step(const float* __restrict__ x_t, const float* __restrict__ eps,
+k_step(const float* x_t, const float* __restrict__ eps,            // x_t and x_out may alias: no __restrict__
        const float* __restrict__ noise, const long long* __restrict__ ts,
        const float* __restrict__ gt, const float* __restrict__ mask,
        const float* __restrict__ noise_next, const long long* __restrict__ ts_next,
-       const float* __restrict__ table, float* __restrict__ x_out, int C, int HWv,
+       const float* __restrict__ table, float* x_out, int C, int HWv,
        long long total, int all_pos) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -135,9 +135,9 @@ k_step(const float* __restrict__ x_t, const float* __restrict__ eps,
 // ddim.py:198-206
 template <int VEC>
 __global__ void __launch_bounds__(256)
-k_ddim_step(const float* __restrict__ x, const float* __restrict__ e_t,
-            const float* __restrict__ noise, float* __restrict__ x_prev,
-            float* __restrict__ pred_x0, float sqrt_a_t, float sqrt_1m_a_t, float sqrt_a_prev,
+k_ddim_step(const float* x, const float* __restrict__ e_t,       // x_prev / pred_x0 may alias x: no __restrict__
+            const float* __restrict__ noise, float* x_prev,
+            float* pred_x0, float sqrt_a_t, float sqrt_1m_a_t, float sqrt_a_prev,
             float dir_coef, float sigma_t, float temperature, long long total) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -159,8 +159,7 @@ k_ddim_step(const float* __restrict__ x, const float* __restrict__ e_t,
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
-k_cfg_combine(const float* __restrict__ eu, const float* __restrict__ ec, float s,
-              float* __restrict__ out, long long total) {
+k_cfg_combine(const float* eu, const float* ec, float s, float* out, long long total) {   // out may alias either input
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     Pack<VEC> a, b, o;

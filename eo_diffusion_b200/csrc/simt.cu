@@ -5,6 +5,7 @@
 //   * weight packing.
 // Reference semantics are cited per kernel (paths under the reference repo root).
 #include "kernels.h"
+#include <algorithm>
 
 namespace eo {
 
@@ -779,6 +780,39 @@ int launch_sinusoid(const int64_t* t, const float* freqs, int B, int half, float
   return EO_OK;
 }
 
+namespace {
+// out[b, :] = table[t[b], :] for 0 <= t[b] < n, NaN otherwise (a timestep outside the precomputed table must not
+// pass silently); rows of `ld` floats, ld % 4 == 0
+__global__ void __launch_bounds__(256)
+k_gather_rows(const float4* __restrict__ table, int n, int ld4, const long long* __restrict__ t, float4* __restrict__ out) {
+  const int b = blockIdx.y;
+  const long long tv = t[b];
+  const bool ok = tv >= 0 && tv < n;
+  const float qn = __int_as_float(0x7fc00000);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ld4; i += gridDim.x * blockDim.x)
+    out[(long long)b * ld4 + i] = ok ? __ldg(table + tv * ld4 + i) : make_float4(qn, qn, qn, qn);
+}
+__global__ void k_iota64(long long* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+}  // namespace
+
+int launch_gather_rows(const float* table, int n, int ld, const int64_t* t, int B, float* out, cudaStream_t st) {
+  EO_REQUIRE(ld % 4 == 0, EO_ERR_ARG, "gather_rows: row length %d is not a multiple of 4", ld);
+  dim3 grid((unsigned)std::min<long long>(ceil_div(ld / 4, 256), 8), (unsigned)B);
+  k_gather_rows<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), n, ld / 4,
+                                      reinterpret_cast<const long long*>(t), reinterpret_cast<float4*>(out));
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+
+int launch_iota64(int64_t* out, int n, cudaStream_t st) {
+  k_iota64<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(reinterpret_cast<long long*>(out), n);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+
 int launch_linear(const float* in, const float* W, const float* bias, const float* bias2,
                   const float* emb_rows, const int64_t* idx, int silu_in, int B, int K, int N,
                   float* out, cudaStream_t st) {
@@ -863,12 +897,115 @@ k_attention_simt(const float* __restrict__ qkv, float* __restrict__ out, int T, 
     for (int d = 0; d < ch; ++d) op[d] = o[d] * inv;
   }
 }
+
+// ---------------------------------------------------------------------------------------
+// Wide heads (head dimension > 64): what the reference's own scripts build -- num_heads = 1, so the
+// middle-block attention has one head of 512 (train.py:50) or 1024 (inference.py:59) channels.
+// One WARP per query row: lane l owns channels l, l + 32, ... of q and of the output accumulator;
+// a block of 8 warps shares K / V tiles of KT keys staged in shared memory as fp32.  Per tile: KT dot
+// products (a 5-step warp reduction each; lane j keeps the logit of key j), one online-softmax update,
+// KT rank-1 updates of o.  Same arithmetic order for fp32 and bf16 inputs (fp32 throughout).
+// ---------------------------------------------------------------------------------------
+constexpr int AW_WARPS = 8;
+
+template <typename TIO, int NC>
+__global__ void __launch_bounds__(AW_WARPS * 32)
+k_attention_wide(const TIO* __restrict__ qkv, TIO* __restrict__ out, int T, int heads, int ch, int ld,
+                 int head_stride, int part_stride, float scale, int KT) {
+  extern __shared__ float aw_smem[];
+  float* Ks = aw_smem;                       // [KT][ch]
+  float* Vs = aw_smem + (size_t)KT * ch;     // [KT][ch]
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * AW_WARPS + warp;
+  const TIO* base = qkv + (long long)b * T * ld + (long long)h * head_stride;
+  float q[NC], o[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int d = lane + 32 * i;
+    q[i] = (qi < T && d < ch) ? to_float(base[(long long)qi * ld + d]) * scale : 0.f;   // q * scale (:475)
+    o[i] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < T; k0 += KT) {
+    const int nk = min(KT, T - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nk * ch; i += AW_WARPS * 32) {
+      const int kk = i / ch, d = i - kk * ch;
+      const TIO* row = base + (long long)(k0 + kk) * ld;
+      Ks[i] = to_float(row[part_stride + d]) * scale;                                    // k * scale
+      Vs[i] = to_float(row[2 * part_stride + d]);
+    }
+    __syncthreads();
+    float sj = -INFINITY;                    // lane j: logit of key k0 + j
+    for (int j = 0; j < nk; ++j) {
+      const float* kr = Ks + (size_t)j * ch + lane;
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (lane + 32 * i < ch) a = fmaf(q[i], kr[32 * i], a);
+      a = warp_sum(a);
+      if (lane == j) sj = a;
+    }
+    const float mn = fmaxf(m, warp_max(sj));
+    const float alpha = expf(m - mn);        // first tile: exp(-inf) = 0
+    const float pj = lane < nk ? expf(sj - mn) : 0.f;
+    l = l * alpha + warp_sum(pj);
+    m = mn;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) o[i] *= alpha;
+    for (int j = 0; j < nk; ++j) {
+      const float p = __shfl_sync(0xffffffffu, pj, j);
+      const float* vr = Vs + (size_t)j * ch + lane;
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (lane + 32 * i < ch) o[i] = fmaf(p, vr[32 * i], o[i]);
+    }
+  }
+  if (qi < T) {
+    const float inv = 1.0f / l;
+    TIO* op = out + ((long long)b * T + qi) * ((long long)heads * ch) + (long long)h * ch;
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (lane + 32 * i < ch) op[lane + 32 * i] = from_float<TIO>(o[i] * inv);
+  }
+}
+
+template <typename TIO>
+int launch_attention_wide_t(const TIO* qkv, TIO* out, int B, int T, int heads, int ch, int ld, int head_stride,
+                            int part_stride, cudaStream_t st) {
+  EO_REQUIRE(ch <= 1024, EO_ERR_ARG, "attention: head dimension %d > 1024 is not supported", ch);
+  const float scale = 1.0f / sqrtf(sqrtf((float)ch));
+  int KT = 8192 / ch;                          // K and V tiles of <= 32 KB each
+  KT = KT > 32 ? 32 : KT;
+  const size_t smem = (size_t)2 * KT * ch * sizeof(float);
+  dim3 grid((unsigned)ceil_div(T, AW_WARPS), (unsigned)heads, (unsigned)B);
+#define EO_AW(NCV)                                                                                                  \
+  do {                                                                                                              \
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attention_wide<TIO, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                       64 * 1024));                                                                 \
+    k_attention_wide<TIO, NCV><<<grid, AW_WARPS * 32, smem, st>>>(qkv, out, T, heads, ch, ld, head_stride,         \
+                                                                   part_stride, scale, KT);                         \
+  } while (0)
+  if (ch <= 128) EO_AW(4); else if (ch <= 256) EO_AW(8); else if (ch <= 512) EO_AW(16); else EO_AW(32);
+#undef EO_AW
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
 }  // namespace
+
+int launch_attention_wide(const void* qkv, void* out, int dt, int B, int T, int heads, int ch, int ld, int head_stride,
+                          int part_stride, cudaStream_t st) {
+  if (dt == DT_F32)
+    return launch_attention_wide_t(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(out), B, T, heads, ch, ld,
+                                   head_stride, part_stride, st);
+  return launch_attention_wide_t(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), B, T,
+                                 heads, ch, ld, head_stride, part_stride, st);
+}
 
 int launch_attention_simt(const float* qkv, float* out, int B, int T, int heads, int ch, int ld,
                           int head_stride, int part_stride, cudaStream_t st) {
-  EO_REQUIRE(ch <= AT_D, EO_ERR_ARG,
-             "attention: head dimension %d > %d is not supported by this build", ch, AT_D);
+  if (ch > AT_D) return launch_attention_wide(qkv, out, DT_F32, B, T, heads, ch, ld, head_stride, part_stride, st);
   float scale = 1.0f / sqrtf(sqrtf((float)ch));
   dim3 grid((unsigned)ceil_div(T, AT_Q), (unsigned)heads, (unsigned)B);
   k_attention_simt<<<grid, AT_Q, 0, st>>>(qkv, out, T, heads, ch, ld, head_stride, part_stride,

@@ -7,32 +7,10 @@
 //
 // Layout: qkv is [B, T, heads*3*64] bf16 -- the qkv 1x1 convolution writes each head's q, k
 // and v padded to 64 channels (zero weight rows), so every head dimension <= 64 runs as
-// d = 64.  One CTA handles up to TWO tiles of 128 queries of one (batch, head) and streams the
-// keys past them in HALF-BLOCKS of 64 (K/V arrive as 128-key TMA tiles, shared by both tiles):
-//   S_t,h = Q_t K_h^T        tcgen05.mma  M=128 N=64 K=64 (operands in smem) -> TMEM S_t[h & 1]
-//   P_t,h = exp2(S_t,h - m)  128 softmax threads per tile, one query row each, ONE pass over S: the
-//                            exponentials are taken against the running reference maximum m while the
-//                            half-block maximum is gathered on the side; only if a logit exceeds m by
-//                            more than 2^8 is the half-block redone (O and l rescaled in place) -- after
-//                            the first few that almost never happens.  P goes back to TENSOR MEMORY as
-//                            packed bf16 pairs (tcgen05.st), never to shared memory.
-//   O_t  += P_t,h V_h        tcgen05.mma  M=128 N=64 K=64 with A = P from TMEM and B = V consumed
-//                            MN-major straight from the [key][d] TMA tile; O_t accumulates in TMEM
-// S and P are double-buffered per tile (2 x 64 + 2 x 32 TMEM columns): S_t,h+2 is issued the moment
-// the softmax hands over P_t,h, so S_t,h+1 is always complete before the softmax threads ask for it
-// and they never wait for the tensor core in steady state.  The bound is then the MUFU pipe, which
-// both tiles' warps share: 128 ex2 per row and 128 keys = 2048 clk per SM for the two tiles.
-// (History, clk per 128-key block measured with eo_debug_conv_trace: two passes over S and P
-// through shared memory 4100; one pass and P in TMEM 3550, of which 960 were the softmax threads
-// waiting for S = Q K^T and the previous P V; strict alternation of the two tiles 4100, because one
-// warp per scheduler only reaches 13 clk per ex2.)
-// Warp roles (352 threads): warp 0 TMA loader, warps 1 and 2 MMA issuers of tile 0 and tile 1 (issuing
-// tcgen05.mma blocks the thread at the tensor pipe's pace -- 64 n + 70 clk for a burst of n, measured
-// with tools/probe_mma_dep.cu -- so one issuer per tile keeps a tile's hand-off from queueing behind the
-// other tile's burst), warps 3..6 softmax of tile 0, warps 7..10 softmax of tile 1.  All hand-offs are
-// mbarriers.
+// d = 64 (wider heads take simt.cu's k_attention_wide).  The kernel (k_attn_tc5) is described at its definition.
 //
-// Roofline: tensor pipe / MUFU.  Algorithmic FLOPs per launch = 4 * B * heads * T^2 * ch.
+// Roofline: MUFU + issue slots (one ex2 per logit, 4*ch FLOPs per logit); algorithmic FLOPs per launch =
+// 4 * B * heads * T^2 * ch.
 #include "kernels.h"
 #include "tc_common.cuh"
 #include <cstdlib>
@@ -43,22 +21,10 @@ namespace {
 
 constexpr int QT = 128;     // queries per tile
 constexpr int KT = 128;     // keys per K/V tile
-constexpr int KH = 64;      // keys per half-block
 constexpr int HD = 64;      // padded head dim
-constexpr int KV_STAGES = 4;
 constexpr int TILE_BYTES = 128 * HD * 2;   // 16 KB
 
-constexpr int OFF_Q = 0;                                    // 2 tiles
-constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
-constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
-constexpr int OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
-// q_full, kv_full[S], kv_empty[S], s_full[2][2], p_full[2][2], o_full[2][2]
-constexpr int N_BARS = 1 + 2 * KV_STAGES + 12;
-constexpr int ATTN_SMEM = OFF_BAR + N_BARS * 8 + 16 + 1024;
-
-// TMEM columns: S (fp32 logits) tile t buffer b at t*128 + b*64; O (fp32) at 256 + t*64;
-// P (bf16 pairs) tile t buffer b at 384 + t*64 + b*32
-constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 384, TM_COLS = 512;
+constexpr uint32_t TM_COLS = 512;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units: P stays <= 2^8
 
 __device__ __forceinline__ float ex2(float x) {
@@ -127,275 +93,20 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// development aid (eo_debug_conv_trace, TRACE instantiation): per-CTA clock64 totals, slot = 0 lifetime,
-// 1 softmax (tile 0, warp 3) waits on S, 2 waits on the P V of two half-blocks ago, 3 time inside the exp
-// pass, 4 redone half-blocks, 5 MMA warp waits on P, 6 MMA warp waits on K/V, 7 half-blocks
+// development aid (eo_debug_conv_trace, TRACE instantiation, -DEO_DEVTOOLS builds): per-CTA clock64 totals
 #define ATR_T0() const long long _t0 = TRACE ? clock64() : 0
 #define ATR_ACC(var) do { if (TRACE) (var) += clock64() - _t0; } while (0)
 
 // LSUM_MMA: the row sum l comes out of the tensor core -- column 63 of V is 1.0 (head dimension < 64: the
 // qkv convolution's bias on that padded row), so column 63 of O accumulates sum_k P_k in fp32, rescaled
 // with O for free.  Otherwise the softmax threads add the rounded P values up themselves.
-template <bool TRACE, bool LSUM_MMA>
-__global__ void __launch_bounds__(352, 1)
-k_attn_tc(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out, int T,
-          int heads, int ch, float scale_log2, long long* trace, int trace_n, int stagger_ns) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + KV_STAGES;
-  uint64_t* s_full = kv_empty + KV_STAGES;   // [tile][buffer]
-  uint64_t* p_full = s_full + 4;             // [tile][buffer], 128 arrivals
-  uint64_t* o_full = p_full + 4;             // [tile][buffer]: the P V that read P buffer b has completed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 4);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long t_entry = TRACE ? clock64() : 0;
-  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  long long* trc = (TRACE && cta_lin < trace_n) ? trace + (long long)cta_lin * 8 : nullptr;
-  const int q0 = blockIdx.x * 2 * QT, h = blockIdx.y, b = blockIdx.z;
-  const int ntiles = (T - q0 > QT) ? 2 : 1;
-  const int nblk = (T + KT - 1) / KT;
-  const int nhalf = (T + KH - 1) / KH;       // half-blocks that hold at least one key
-  const int cq = h * 3 * HD, ck = cq + HD, cv = cq + 2 * HD;
-
-  if (warp == 0 && lane == 0) {
-    tc::tma_prefetch_desc(&map_qkv);
-    tc::mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], ntiles); }
-    for (int i = 0; i < 4; ++i) {
-      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 128); tc::mbar_init(&o_full[i], 1);
-    }
-    tc::fence_barrier_init();
-  }
-  if (warp == 1) { tc::tmem_alloc(tmem_ptr, TM_COLS); tc::tmem_relinquish(); }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-
-  // Loader and MMA warps run their loops warp-uniformly and issue from one elected lane (under
-  // `if (lane == 0)` ptxas wraps every TMA / MMA instruction in a read-lane loop).
-  if (warp == 0) {
-    if (tc::elect_one()) {
-      tc::mbar_arrive_expect_tx(q_full, ntiles * TILE_BYTES);
-      for (int t = 0; t < ntiles; ++t)
-        tc::tma_load_3d(smem + OFF_Q + t * TILE_BYTES, &map_qkv, q_full, cq, q0 + t * QT, b);
-    }
-    __syncwarp();
-    uint32_t s = 0, ph = 0;
-    for (int j = 0; j < nblk; ++j) {
-      tc::mbar_wait(&kv_empty[s], ph ^ 1);
-      if (tc::elect_one()) {
-        tc::mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-        tc::tma_load_3d(smem + OFF_K + s * TILE_BYTES, &map_qkv, &kv_full[s], ck, j * KT, b);
-        tc::tma_load_3d(smem + OFF_V + s * TILE_BYTES, &map_qkv, &kv_full[s], cv, j * KT, b);
-      }
-      __syncwarp();
-      if (++s == KV_STAGES) { s = 0; ph ^= 1; }
-    }
-  } else if (warp <= 2) {
-    if (warp - 1 < ntiles) {
-    const int t = warp - 1;
-    constexpr uint32_t idesc_s = tc::make_idesc_bf16(128, KH, 0, 0);   // Q (K-major) x K (K-major)
-    constexpr uint32_t idesc_o = tc::make_idesc_bf16(128, HD, 0, 1);   // P (TMEM) x V (MN-major)
-    const uint64_t qdesc0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF_Q));
-    const uint64_t kdesc0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF_K));
-    const uint64_t vdesc0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF_V));
-    constexpr uint32_t TILE16 = TILE_BYTES >> 4, HALF16 = (KH * 128) >> 4;
-    // S_t,hb = Q_t K_hb^T into S_t[hb & 1]; K half-block hb = rows 64*(hb & 1).. of the K tile in `stage`
-    auto issue_s = [&](int hb, uint32_t stage) {
-      if (tc::elect_one()) {
-        const uint64_t qdesc = qdesc0 + (uint64_t)(t * TILE16);
-        const uint64_t kdesc = kdesc0 + (uint64_t)(stage * TILE16 + (hb & 1) * HALF16);
-        const uint32_t d = tmem + TM_S + t * 128 + (hb & 1) * 64;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          tc::umma_f16_ss(d, tc::desc_advance(qdesc, k * 32), tc::desc_advance(kdesc, k * 32), idesc_s, k != 0 ? 1u : 0u);
-        tc::umma_commit(&s_full[t * 2 + (hb & 1)]);
-      }
-      __syncwarp();
-    };
-    // O_t (+)= P_t,hb V_hb in TMEM; the softmax threads rescale O_t in place when m moves
-    auto issue_pv = [&](int hb, uint32_t stage, bool release_kv) {
-      if (tc::elect_one()) {
-        const uint64_t vdesc = vdesc0 + (uint64_t)(stage * TILE16 + (hb & 1) * HALF16);
-        const uint32_t d = tmem + TM_O + t * 64;
-        const uint32_t pa = tmem + TM_P + t * 64 + (hb & 1) * 32;
-#pragma unroll
-        for (int k = 0; k < KH / 16; ++k)      // A: 16 keys = 8 packed columns of P; B: 16 rows of 128 B of V
-          umma_f16_ts(d, pa + k * 8, tc::desc_advance(vdesc, k * 16 * 128), idesc_o, (hb != 0 || k != 0) ? 1u : 0u);
-        tc::umma_commit(&o_full[t * 2 + (hb & 1)]);
-        if (release_kv) tc::umma_commit(&kv_empty[stage]);     // K_j, V_j consumed by this tile
-      }
-      __syncwarp();
-    };
-    long long tr_p = 0, tr_kv = 0;
-    tc::mbar_wait(q_full, 0);
-    tc::mbar_wait(&kv_full[0], 0);
-    tc::tc_fence_after();
-    for (int hb = 0; hb < 2 && hb < nhalf; ++hb) issue_s(hb, 0);
-    uint32_t st = 0, ph = 0;                 // stage / phase of the K/V tile of half-block hb
-    for (int hb = 0; hb < nhalf; ++hb) {
-      // the K/V tile that half-block hb + 2 lives in (the next one)
-      uint32_t st1 = st + 1, ph1 = ph;
-      if (st1 == KV_STAGES) { st1 = 0; ph1 ^= 1; }
-      const bool more = hb + 2 < nhalf;
-      if (more && (hb & 1) == 0) {
-        { ATR_T0(); tc::mbar_wait(&kv_full[st1], ph1); ATR_ACC(tr_kv); }
-        tc::tc_fence_after();
-      }
-      // p_full: P_t,hb is in TMEM and S_t[hb & 1] has been consumed -> refill that S buffer first (the
-      // softmax of half-block hb + 2 needs it a whole exp pass from now), then this half-block's P V
-      { ATR_T0(); tc::mbar_wait(&p_full[t * 2 + (hb & 1)], (hb >> 1) & 1); ATR_ACC(tr_p); }
-      tc::tc_fence_after();
-      if (more) issue_s(hb + 2, st1);
-      issue_pv(hb, st, (hb & 1) == 1 || hb == nhalf - 1);
-      if (hb & 1) { st = st1; ph = ph1; }
-    }
-    if (trc && warp == 1 && lane == 0) { trc[5] = tr_p; trc[6] = tr_kv; trc[7] = nhalf; }
-    }
-  } else if (warp < 3 + 4 * ntiles) {
-    // ---- softmax / output warps: thread <-> query row of tile t
-    const int t = (warp - 3) >> 2;
-    const int qd = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int row = qd * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const uint32_t s_base = tmem + lane_addr + TM_S + t * 128;
-    const uint32_t o_addr = tmem + lane_addr + TM_O + t * 64;
-    const uint32_t p_base = tmem + lane_addr + TM_P + t * 64;
-    float m = -INFINITY, l = 0.f;       // m: reference maximum (log2 domain) of everything accumulated so far
-    long long tr_s = 0, tr_o = 0, tr_exp = 0, tr_redo = 0;
-    if (t == 1 && stagger_ns > 0) __nanosleep(stagger_ns);
-
-    for (int hb = 0; hb < nhalf; ++hb) {
-      const int buf = hb & 1;
-      const uint32_t s_addr = s_base + buf * 64, p_addr = p_base + buf * 32;
-      { ATR_T0(); tc::mbar_wait(&s_full[t * 2 + buf], (hb >> 1) & 1); ATR_ACC(tr_s); }
-      tc::tc_fence_after();
-      const int nvalid = T - hb * KH;          // < KH only in a ragged last half-block
-      uint32_t v[64];
-      // the 64 logits of this row: one batch of tcgen05.ld, masked past the last key
-      auto load_s = [&]() {
-        tc::tmem_ld_32x32(s_addr, v);
-        tc::tmem_ld_32x32(s_addr + 32, v + 32);
-        tc::tmem_ld_wait();
-        if (nvalid < KH) {
-#pragma unroll
-          for (int i = 0; i < KH; ++i)
-            if (i >= nvalid) v[i] = 0xff800000u;   // -inf
-        }
-      };
-      auto raw_max = [&]() -> float {
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int i = 0; i < KH; i += 2)
-          mx[(i >> 1) & 3] = max3(mx[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-        return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      };
-      // P = exp2(S*scale - mref) -> packed bf16 pairs (low half = even key) -> TMEM; returns the row sum
-      // (0 when the tensor core gathers it).  (ex2.approx.f16x2 is no shortcut: it compiles to two
-      // MUFU.EX2.F16, 16 clk per pair like two fp32 MUFU.EX2 -- tools/probe_mufu.cu.)
-      auto exp_store = [&](float mref) -> float {
-        float rs0 = 0.f, rs1 = 0.f;
-        uint32_t pk[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float p0 = ex2(fmaf(__uint_as_float(v[2 * k]), scale_log2, -mref));
-          const float p1 = ex2(fmaf(__uint_as_float(v[2 * k + 1]), scale_log2, -mref));
-          if (!LSUM_MMA) { rs0 += p0; rs1 += p1; }
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-          pk[k] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-        tmem_st_32x32(p_addr, pk);
-        return rs0 + rs1;
-      };
-      // rescale O_t and l when the reference maximum moves (every P V issued so far must have landed)
-      auto move_max = [&](float cm) {
-        const float m_new = fmaxf(m, cm);
-        const float alpha = ex2(m - m_new);          // first half-block: ex2(-inf) = 0
-        m = m_new;
-        l *= alpha;
-        if (hb > 0) {
-          tc::mbar_wait(&o_full[t * 2 + (buf ^ 1)], ((hb - 1) >> 1) & 1);    // P V of half-block hb - 1
-          tc::tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < HD; c += 32) {
-            uint32_t o[32];
-            tc::tmem_ld_32x32(o_addr + c, o);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32(o_addr + c, o);
-          }
-        }
-      };
-      // P buffer `buf` is free once the P V of half-block hb - 2 has read it (issued a whole exp pass ago)
-      if (hb >= 2) { ATR_T0(); tc::mbar_wait(&o_full[t * 2 + buf], ((hb >> 1) - 1) & 1); ATR_ACC(tr_o); tc::tc_fence_after(); }
-      ATR_T0();
-      load_s();
-      const float cm = raw_max() * scale_log2;
-      // warp-uniform decision (the TMEM accesses are warp-collective)
-      if (__any_sync(0xffffffffu, cm > m + RESCALE_THRESHOLD)) {
-        move_max(cm);
-        if (TRACE && hb > 0) ++tr_redo;
-      }
-      l += exp_store(m);
-      ATR_ACC(tr_exp);
-      // hand P_t,hb (and the consumed S buffer, and the possibly rescaled O_t) to the MMA warp
-      tmem_st_wait();
-      tc::tc_fence_before();
-      tc::mbar_arrive(&p_full[t * 2 + buf]);
-    }
-    if (trc && warp == 3 && lane == 0) { trc[1] = tr_s; trc[2] = tr_o; trc[3] = tr_exp; trc[4] = tr_redo; }
-    // both P V chains end in o_full: the last two half-blocks
-    if (nhalf >= 2) tc::mbar_wait(&o_full[t * 2 + ((nhalf - 2) & 1)], ((nhalf - 2) >> 1) & 1);
-    tc::mbar_wait(&o_full[t * 2 + ((nhalf - 1) & 1)], ((nhalf - 1) >> 1) & 1);
-    tc::tc_fence_after();
-    const int qi = q0 + t * QT + row;
-    __nv_bfloat16* op = out + ((long long)b * T + qi) * (heads * ch) + h * ch;
-    float inv = 1.0f / l;
-#pragma unroll
-    for (int c = HD - 32; c >= 0; c -= 32) {      // upper half first: it holds the row sum
-      uint32_t o[32];
-      tc::tmem_ld_32x32(o_addr + c, o);
-      tc::tmem_ld_wait();
-      if (LSUM_MMA && c == HD - 32) inv = 1.0f / __uint_as_float(o[31]);
-      if (qi < T) {
-#pragma unroll
-        for (int d = 0; d < 32; d += 8) {
-          if (c + d < ch) {
-            uint4 w4;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              h2[e] = __floats2bfloat162_rn(__uint_as_float(o[d + 2 * e]) * inv,
-                                            __uint_as_float(o[d + 2 * e + 1]) * inv);
-            *reinterpret_cast<uint4*>(op + c + d) = w4;
-          }
-        }
-      }
-    }
-    tc::tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem, TM_COLS);
-  }
-  if (trc && threadIdx.x == 0) trc[0] = clock64() - t_entry;
-}
-
 
 // =====================================================================================================
 // k_attn_tc5: FOUR query tiles per CTA, 32-key quarter-blocks.
 //
-// The two-tile kernel above keeps the MUFU pipe 61 % busy (profiles/r01c_attn_tc_v4_ncu.txt: xu 61 %, tensor
-// 30 %; trace: 1740 clk per 64-key half-block of which the exp pass is 1150 and 400 are waits): with one warp of
-// each tile per scheduler, the fixed latencies of every hand-off (a satisfied mbarrier.try_wait alone costs
+// A first kernel with TWO query tiles per CTA and 64-key half-blocks kept the MUFU pipe 61 % busy
+// (profiles/r01c_attn_tc_v4_ncu.txt: xu 61 %, tensor 30 %; trace: 1740 clk per 64-key half-block of which the exp
+// pass is 1150 and 400 are waits): with one warp of each tile per scheduler, the fixed latencies of every hand-off (a satisfied mbarrier.try_wait alone costs
 // ~100 clk, tcgen05.ld, the maximum tree, the vote, tcgen05.st + wait) leave the other warp alone on the pipe.
 // Here each scheduler holds FOUR softmax warps (one per tile):
 //   * tensor memory per tile: two 32-column S buffers (fp32 logits of one 32-key quarter-block) + 64 columns
@@ -734,37 +445,27 @@ void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
 
 int tc_attn_launch(const TcAttnPlan* pl, int B, cudaStream_t st) {
   static bool attr_set = false;
-  static int stagger = 0, use_v4 = 0;
   if (!attr_set) {
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
+#ifdef EO_DEVTOOLS
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
-    const char* e = std::getenv("EO_ATTN_STAGGER");
-    stagger = e ? atoi(e) : 0;
-    e = std::getenv("EO_ATTN_V4");            // A/B switch: the two-tile kernel
-    use_v4 = e ? atoi(e) : 0;
+#endif
     attr_set = true;
   }
   const TcAttnParams& p = pl->p;
   // logits = (q . k) * ch^-1/2 ; softmax evaluated with exp2
   float scale_log2 = (1.0f / sqrtf((float)p.ch)) * 1.4426950408889634f;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-  if (use_v4) {
-    dim3 grid((unsigned)ceil_div(p.T, 2 * QT), (unsigned)p.heads, (unsigned)B);
-    auto kern = g_attn_trace ? (p.ones_col ? k_attn_tc<true, true> : k_attn_tc<true, false>)
-                             : (p.ones_col ? k_attn_tc<false, true> : k_attn_tc<false, false>);
-    kern<<<grid, 352, ATTN_SMEM, st>>>(pl->map, out, p.T, p.heads, p.ch, scale_log2, g_attn_trace, g_attn_trace_n, stagger);
-  } else {
-    dim3 grid((unsigned)ceil_div(p.T, NT5 * QT), (unsigned)p.heads, (unsigned)B);
-    auto kern = g_attn_trace ? (p.ones_col ? k_attn_tc5<true, true> : k_attn_tc5<true, false>)
-                             : (p.ones_col ? k_attn_tc5<false, true> : k_attn_tc5<false, false>);
-    kern<<<grid, ATTN5_THREADS, ATTN5_SMEM, st>>>(pl->map, out, p.T, p.heads, p.ch, scale_log2, g_attn_trace, g_attn_trace_n);
-  }
+  dim3 grid((unsigned)ceil_div(p.T, NT5 * QT), (unsigned)p.heads, (unsigned)B);
+#ifdef EO_DEVTOOLS
+  auto kern = g_attn_trace ? (p.ones_col ? k_attn_tc5<true, true> : k_attn_tc5<true, false>)
+                           : (p.ones_col ? k_attn_tc5<false, true> : k_attn_tc5<false, false>);
+#else
+  auto kern = p.ones_col ? k_attn_tc5<false, true> : k_attn_tc5<false, false>;
+#endif
+  kern<<<grid, ATTN5_THREADS, ATTN5_SMEM, st>>>(pl->map, out, p.T, p.heads, p.ch, scale_log2, g_attn_trace, g_attn_trace_n);
   EO_CHECK_LAUNCH();
   return EO_OK;
 }

@@ -283,7 +283,9 @@ __device__ __forceinline__ bool elect_one() {
 }  // namespace tc
 
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
+// elem_strides (optional, rank entries): traversal stride per dimension; a box extent of N * stride then loads N elements
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box);
+                     const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
+                     const uint32_t* elem_strides = nullptr);
 
 }  // namespace eo

@@ -1,8 +1,8 @@
-// Persistent implicit-GEMM convolution on tcgen05 (third generation of tc_conv.cu's kernel).
+// Persistent implicit-GEMM convolution on tcgen05 (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
 //
-// Same GEMM view and fusions as tc_conv.cu (reference backbones/unet_openai.py: ResBlock :316,
+// GEMM view and fusions as stated in tc_conv.cu (reference backbones/unet_openai.py: ResBlock :316,
 // :342,:353,:382,:385; AttentionBlock :412,:422,:433; Downsample :262; Upsample :227; th.cat
-// :773), restructured after the per-CTA timeline measured on B200
+// :773).  Structure, after the per-CTA timeline of a one-tile-per-CTA first version measured on B200
 // (profiles/r01_conv_tc_pair_cta_timeline.txt: the main loop ran at tensor-pipe rate but 55 % of
 // every CTA's life was set-up, first-load latency, a store-bound epilogue and tear-down):
 //
@@ -212,7 +212,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         const CUtensorMap* ma = en.seg == 0 ? &mapA0 : (en.seg == 1 ? &mapA1 : &mapA2);
         if (!en.gn && tc::elect_one()) {
           const int dh = (int)(short)(en.dhw & 0xffff), dw = en.dhw >> 16;
-          const int cw = t.w0 + (en.patch ? -1 : dw), chh = t.h0 + (en.patch ? -1 : dh);
+          const int cw = t.w0 * en.sc + (en.patch ? -1 : dw), chh = t.h0 * en.sc + (en.patch ? -1 : dh);
           const uint32_t bytes = en.patch ? PATCH_BYTES : PLAIN_BYTES;
           uint8_t* dst = smem_a + ra.i * A_STAGE;
           // one arrival per phase: the leader's producer, which posts the byte count of BOTH CTAs' loads
@@ -511,6 +511,8 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const int row = q * 32 + lane;
     const int et = ew * 32 + lane;                 // 0..255
     const int nn = row / (g.bw * g.bh);
+    const int pix_w = row % g.bw, pix_h = (row / g.bw) % g.bh;      // this thread's pixel inside the tile
+    const bool to_nchw = ep.out_nchw != nullptr;
     // the warp's 32 rows as a sub-box of the tile
     const int row0 = q * 32;
     const int sub_w = row0 % g.bw, sub_h = (row0 / g.bw) % g.bh, sub_n = row0 / (g.bw * g.bh);
@@ -621,13 +623,24 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
               }
             }
           }
+          if (to_nchw) {
+            // network output: fp32 planes, 8 consecutive pixels of a row per 8 lanes (32-byte segments)
+            if (valid) {
+              float* op = ep.out_nchw + (((long long)n_img * ep.out_nchw_C) * g.H + (t.h0 + pix_h)) * g.W + t.w0 + pix_w;
+              const long long plane = (long long)g.H * g.W;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint4 o;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+              for (int j = 0; j < 32; ++j)
+                if (half * 32 + j < ep.out_nchw_C) op[(half * 32 + j) * plane] = f[j];
+            }
+          } else {
 #pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) h2[e2] = __floats2bfloat162_rn(f[k * 8 + e2 * 2], f[k * 8 + e2 * 2 + 1]);
-            *reinterpret_cast<uint4*>(stg + row_off + ((((uint32_t)(half * 4 + k)) ^ swz) << 4)) = o;
+            for (int k = 0; k < 4; ++k) {
+              uint4 o;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e2 = 0; e2 < 4; ++e2) h2[e2] = __floats2bfloat162_rn(f[k * 8 + e2 * 2], f[k * 8 + e2 * 2 + 1]);
+              *reinterpret_cast<uint4*>(stg + row_off + ((((uint32_t)(half * 4 + k)) ^ swz) << 4)) = o;
+            }
           }
           if (TRACE) tr_e3 += clock64() - t_e3;
         }
@@ -637,7 +650,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         }
         tc::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !to_nchw) {
           tma_store_4d(&mapOut, stg + row0 * 128, t.nbase + c * 64, t.w0 + sub_w, t.h0 + sub_h, t.n0 + sub_n);
           bulk_commit();
         }
@@ -716,24 +729,13 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+#ifdef EO_DEVTOOLS
 static bool env_flag(const char* name, bool dflt) {
   const char* e = std::getenv(name);
   if (!e || !e[0]) return dflt;
   return e[0] != '0';
 }
-
-bool tc_conv3_enabled() {
-  static int v = -1;
-  if (v < 0) v = env_flag("EO_CONV_V2", false) ? 0 : 1;
-  return v != 0;
-}
-
-bool tc_conv_patch_supported(int H, int W) {
-  static int v = -1;
-  if (v < 0) v = env_flag("EO_CONV_PATCH", true) ? 1 : 0;
-  return tc_conv3_enabled() && v != 0 && H % 16 == 0 && W % 8 == 0;
-}
-
+#endif
 
 int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
   Geom3 g;
@@ -751,6 +753,8 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
   EO_REQUIRE(!(p.stats && g.bw * g.bh < 32), EO_ERR_ARG,
              "tc_conv3: fused GroupNorm statistics need at least 32 pixels per image (%dx%d)", p.H, p.W);
   EO_REQUIRE(!p.out_f32 && !p.res_f32, EO_ERR_ARG, "tc_conv3: bf16 outputs and residuals only");
+  EO_REQUIRE(!p.out_nchw_C || (p.Cout == 64 && p.out_nchw_C >= 1 && p.out_nchw_C <= 64 && !p.stats && !p.out_sw), EO_ERR_ARG,
+             "tc_conv3: the NCHW fp32 output takes one 64-wide channel tile, no statistics, no strided view");
   g.tiles_w = p.W / g.bw; g.tiles_h = p.H / g.bh;
   g.d_tw.set((unsigned)g.tiles_w); g.d_th.set((unsigned)g.tiles_h);
   pl->g3 = g;
@@ -762,9 +766,12 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
   for (int s = 0; s < p.nseg; ++s) {
     const TcConvSeg& sg = p.seg[s];
     EO_REQUIRE(sg.C % BK == 0, EO_ERR_ARG, "tc_conv3: segment channels %d must be a multiple of 64", sg.C);
-    uint64_t dims[4] = {(uint64_t)sg.C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)sg.Bt};
-    uint64_t str[3] = {(uint64_t)sg.C * 2, (uint64_t)p.W * sg.C * 2, (uint64_t)p.H * p.W * sg.C * 2};
-    uint32_t box[4] = {(uint32_t)BK, (uint32_t)g.bw, (uint32_t)g.bh, (uint32_t)g.bn};
+    EO_REQUIRE(sg.stride == 1 || (sg.stride == 2 && !sg.patch), EO_ERR_ARG, "tc_conv3: segment stride %d", sg.stride);
+    const uint64_t sW = (uint64_t)p.W * sg.stride, sH = (uint64_t)p.H * sg.stride;      // the segment's own grid
+    uint64_t dims[4] = {(uint64_t)sg.C, sW, sH, (uint64_t)sg.Bt};
+    uint64_t str[3] = {(uint64_t)sg.C * 2, sW * sg.C * 2, sH * sW * sg.C * 2};
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)(g.bw * sg.stride), (uint32_t)(g.bh * sg.stride), (uint32_t)g.bn};
+    uint32_t est[4] = {1u, (uint32_t)sg.stride, (uint32_t)sg.stride, 1u};
     EO_REQUIRE(!sg.gn_scale || sg.patch, EO_ERR_ARG, "tc_conv3: GroupNorm can only be folded into a halo-patch segment");
     EO_REQUIRE(!sg.gn_scale || (sg.gn_shift && sg.gn_ld % 4 == 0 && sg.gn_coff % 8 == 0), EO_ERR_ARG,
                "tc_conv3: GroupNorm rows must be 16-byte aligned");
@@ -775,12 +782,12 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
                    "tc_conv3: a patch segment is a plain 3x3 window");
       box[1] = PATCH_W; box[2] = PATCH_H; box[3] = 1;
     }
-    int rc = encode_tmap_bf16(&pl->mapA[s], sg.ptr, 4, dims, str, box);
+    int rc = encode_tmap_bf16(&pl->mapA[s], sg.ptr, 4, dims, str, box, est);
     if (rc != EO_OK) return rc;
     if (sg.patch) {
       // K order of a patch segment: (64-channel block, tap, channel)
       for (int c0 = 0; c0 < sg.C; c0 += BK) {
-        KEnt3 e{}; e.seg = s; e.c0 = c0; e.patch = 1; e.kofs = kofs;
+        KEnt3 e{}; e.seg = s; e.c0 = c0; e.patch = 1; e.kofs = kofs; e.sc = 1;
         e.gn = sg.gn_scale ? (sg.silu ? 2 : 1) : 0; e.gnc = sg.gn_coff + c0;
         tab.push_back(e);
         kofs += 9 * BK;
@@ -788,7 +795,7 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
     } else {
       for (int t = 0; t < sg.ntaps; ++t)
         for (int c0 = 0; c0 < sg.C; c0 += BK) {
-          KEnt3 e{}; e.seg = s; e.c0 = c0; e.dhw = ((int)sg.dh[t] & 0xffff) | ((int)sg.dw[t] << 16); e.dn = sg.dn[t]; e.kofs = kofs;
+          KEnt3 e{}; e.seg = s; e.c0 = c0; e.dhw = ((int)sg.dh[t] & 0xffff) | ((int)sg.dw[t] << 16); e.dn = sg.dn[t]; e.kofs = kofs; e.sc = sg.stride;
           e.gn = sg.gn_scale ? (sg.silu ? 2 : 1) : 0; e.gnc = sg.gn_coff + c0;
           tab.push_back(e);
           kofs += BK;
@@ -818,7 +825,8 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
     const uint32_t sw = (uint32_t)(g.bw < 32 ? g.bw : 32);
     const uint32_t sh = (uint32_t)(g.bh < (int)(32 / sw) ? g.bh : (int)(32 / sw));
     uint32_t sbox[4] = {(uint32_t)BK, sw, sh, 32 / (sw * sh)};
-    int rc = encode_tmap_bf16(&pl->mapOut, p.out, 4, dims, str, sbox);
+    // (an NCHW-output conv never stores through this map; it still needs a valid base address)
+    int rc = encode_tmap_bf16(&pl->mapOut, p.out_nchw_C ? p.Wp : p.out, 4, dims, str, sbox);
     if (rc != EO_OK) return rc;
     pl->mapRes = pl->mapOut;
     if (p.residual) {
@@ -830,7 +838,6 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
   cudaError_t e = cudaMalloc(&pl->d_kblks, tab.size() * sizeof(KEnt3));
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_kblks, tab.data(), tab.size() * sizeof(KEnt3), cudaMemcpyHostToDevice);
   EO_REQUIRE(e == cudaSuccess, EO_ERR_CUDA, "tc_conv3: operand table upload failed: %s", cudaGetErrorString(e));
-  pl->v3 = true;
   return EO_OK;
 }
 
@@ -838,7 +845,7 @@ static long long* g_trace3 = nullptr;
 static int g_trace3_n = 0;
 void tc_conv3_set_trace(long long* dev_buf, int n) { g_trace3 = dev_buf; g_trace3_n = n; }
 
-int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
+int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st, float* out_nchw) {
   static bool attr_set = false;
   const TcConvParams& p = pl->p;
   Geom3 g = pl->g3;
@@ -850,16 +857,11 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
   bool any_gn = false, any_raw = false;
   for (int s = 0; s < p.nseg; ++s) { if (p.seg[s].gn_scale) any_gn = true; else any_raw = true; }
   int SAR = any_raw ? (any_gn ? 2 : 3) : 0, SAG = any_gn ? (any_raw ? 2 : 3) : 0;
-  if (const char* e = std::getenv("EO_SA")) {      // experiment: operand-A stages of a single-kind conv
-    const int v = atoi(e);
-    if (v >= 2 && v <= SA_MAX && !(any_gn && any_raw)) { if (any_raw) SAR = v; else SAG = v; }
-  }
   const int fixed = (SAR + SAG) * A_STAGE + Smem::VAR_OFF + (has_res ? 2 * STG_BYTES : 0);
   // narrow tiles: three weight tiles (one kernel row of a patch) per stage, see the MMA warp
   bool any_patch = false;
   for (int s = 0; s < p.nseg; ++s) any_patch |= p.seg[s].patch != 0;
   int TPB = (any_patch && BN <= 192) ? 3 : 1;
-  if (const char* e = std::getenv("EO_TPB")) { if (any_patch && (atoi(e) == 1 || atoi(e) == 3)) TPB = atoi(e); }
   const int b_stage = TPB * b_bytes;
   int SB = (SMEM_LIMIT - 1024 - fixed) / b_stage;
   if (SB > MAX_SB) SB = MAX_SB;
@@ -867,7 +869,9 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
   const int dyn = fixed + SB * b_stage + 1024;
   if (!attr_set) {
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+#ifdef EO_DEVTOOLS
     EO_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+#endif
     attr_set = true;
   }
   const int tiles_n = (int)ceil_div(B, g.bn);
@@ -880,6 +884,8 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
   Epi3 ep{};
   ep.bias = p.bias; ep.bias_nc = p.bias_nc; ep.ld_bias_nc = p.ld_bias_nc; ep.stats = p.stats; ep.Cout = p.Cout;
   ep.has_res = has_res ? 1 : 0;
+  EO_REQUIRE((p.out_nchw_C > 0) == (out_nchw != nullptr), EO_ERR_ARG, "tc_conv3: NCHW output pointer / plan mismatch");
+  ep.out_nchw = out_nchw; ep.out_nchw_C = p.out_nchw_C;
   for (int s = 0; s < 3; ++s) {
     const bool on = s < p.nseg && p.seg[s].gn_scale != nullptr;
     ep.gn_scale[s] = on ? p.seg[s].gn_scale : nullptr;
@@ -889,8 +895,10 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
     ep.gn_C[s] = on ? p.seg[s].C : 0;
     ep.any_gn |= on ? 1 : 0;
   }
+#ifdef EO_DEVTOOLS
   ep.trace = g_trace3; ep.trace_n = g_trace3_n;
   ep.trace_ext = env_flag("EO_TRACE_EXT", false) ? 1 : 0;
+#endif
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * ncl));
   cfg.blockDim = dim3(NUM_THREADS);
@@ -900,7 +908,11 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+#ifdef EO_DEVTOOLS
   auto kern = g_trace3 ? k_conv_tc3<true> : k_conv_tc3<false>;
+#else
+  auto kern = k_conv_tc3<false>;
+#endif
   EO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA[0], pl->mapA[1], pl->mapA[2], pl->mapB, pl->mapOut,
                                    pl->mapRes, (const KEnt3*)pl->d_kblks, pl->nkb, g, B, BN, SB, TPB, SAR, SAG, n_work, n_ntiles, ep));
   return EO_OK;

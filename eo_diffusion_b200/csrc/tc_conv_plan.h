@@ -1,26 +1,17 @@
-// Plan object shared by the two tensor-core convolution kernels (tc_conv.cu: one tile per CTA,
-// kept for A/B comparison behind EO_CONV_V2=1; tc_conv3.cu: persistent, the default).
+// Plan object of the tensor-core convolution (tc_conv3.cu; host helpers in tc_conv.cu).
 #pragma once
 #include <cuda.h>
 #include "kernels.h"
 
 namespace eo {
 
-// ---- tc_conv.cu
-struct KBlk { int seg; int c0; int dh_dw; int dn; };   // dh: low 16 bits, dw: high 16 bits
-struct TileGeom {
-  int bw, bh, bn;          // box extents, bw*bh*bn == 128
-  int tiles_w, tiles_h;
-  int H, W;
-};
-
-// ---- tc_conv3.cu
 // One operand-A load of the K loop: a plain 128-pixel tile shifted by (dh, dw) in image plane dn
 // (one weight tile follows), or a halo patch (nine weight tiles follow, one per tap).
 //   gn: 0 = operand loaded by TMA as is, 1 = GroupNorm affine folded in (x*scale + shift), 2 = affine + SiLU:
 //   the transform warps load the patch from global memory, apply it and write the operand stage;
-//   gnc = first channel of this load in the scale/shift rows
-struct KEnt3 { int seg, c0, dhw, dn, kofs, patch, gn, gnc; };   // dhw: dh in the low 16 bits, dw in the high
+//   gnc = first channel of this load in the scale/shift rows;
+//   sc = 1, or 2 for a stride-2 source (the tile origin is doubled: the segment's tensor map walks every second pixel)
+struct KEnt3 { int seg, c0, dhw, dn, kofs, patch, gn, gnc, sc; };   // dhw: dh in the low 16 bits, dw in the high
 // division by a launch-time constant as multiply-high + shift (exact for dividends below 2^31): the generic
 // integer division sequence is ~35 dependent instructions, and every warp role decodes a tile index per tile
 struct FastDiv {
@@ -48,6 +39,8 @@ struct Epi3 {
   int ld_bias_nc;
   double* stats;            // [B, Cout, 2] (sum, sum of squares) accumulated with atomics, or null
   int Cout, has_res;
+  float* out_nchw;          // head convolution: the first out_nchw_C channels go straight to this NCHW fp32 tensor
+  int out_nchw_C;           // (the network output, unet_openai.py:780) instead of the bf16 NHWC staging / TMA store
   const float* gn_scale[3];   // per segment: [B, gn_ld] rows of the GroupNorm it reads through, or null
   const float* gn_shift[3];
   int gn_ld[3];
@@ -65,18 +58,14 @@ struct TcConvPlan {
   CUtensorMap mapOut, mapRes;   // v3: TMA store of the output, TMA load of the residual
   void* d_kblks = nullptr;
   int nkb = 0;
-  TileGeom g{};
   Geom3 g3{};
   int bn_tile = 128;
-  bool pair = true;
-  bool v3 = false;
   TcConvParams p;
 };
 
-bool tc_conv3_enabled();
 void tc_conv_tile_geom(int H, int W, int* bw, int* bh, int* bn);
 int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl);
-int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st);
+int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st, float* out_nchw);
 void tc_conv3_set_trace(long long* dev_buf, int n_ctas);
 
 }  // namespace eo

@@ -8,6 +8,8 @@ the per-pixel update of every step run in libeo_b200 (`eo_unet_forward`, `eo_ddi
 `eo_cfg_combine`)."""
 from __future__ import annotations
 
+import contextlib
+
 import numpy as np
 import torch
 
@@ -154,6 +156,17 @@ class DDIMSampler(object):
         time_range = np.flip(timesteps)
         total_steps = timesteps.shape[0]
         print(f"Running DDIM Sampling with {total_steps} timesteps")
+        # every step value is <= ddpm_num_timesteps (util.py:63-77 adds 1): hoist the embedding path
+        tables = getattr(self.model.model, "time_tables", None)
+        hoist = tables(self.ddpm_num_timesteps + 1) if tables is not None else contextlib.nullcontext()
+        with hoist:
+            return self._ddim_loop(img, cond, time_range, total_steps, b, device, intermediates, callback, img_callback,
+                                   log_every_t, temperature, noise_dropout, quantize_denoised, score_corrector,
+                                   corrector_kwargs, unconditional_guidance_scale, unconditional_conditioning)
+
+    def _ddim_loop(self, img, cond, time_range, total_steps, b, device, intermediates, callback, img_callback,
+                   log_every_t, temperature, noise_dropout, quantize_denoised, score_corrector, corrector_kwargs,
+                   unconditional_guidance_scale, unconditional_conditioning):
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
             ts = torch.full((b,), int(step), device=device, dtype=torch.long)

@@ -8,6 +8,7 @@ computes with the reference's own torch ops.  The UNet call goes through `self.m
 (normally `eo_diffusion_b200.UNetModel`, i.e. libeo_b200 again)."""
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 
@@ -179,7 +180,10 @@ class EODiffusion(nn.Module):
         clip = int(bool(clipped_reverse_diffusion))
         pngs = (write_pngs is None) or bool(write_pngs)
 
-        with torch.cuda.device(dev):
+        # every UNet call of the loop uses a timestep value in [0, T): hoist the embedding path
+        tables = getattr(self.model, "time_tables", None)
+        hoist = tables(T) if (tables is not None and y is None) else contextlib.nullcontext()
+        with torch.cuda.device(dev), hoist:
             st = _lib.stream_ptr
             noise = torch.randn_like(x_t).to(dev)
             if sum_mode:   # mix of the first iteration (model.py:58-60)

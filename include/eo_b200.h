@@ -95,7 +95,8 @@ EO_API int eo_unet_weight_shape(const eo_unet* u, int index, int64_t shape[4]);
 
 /* Hand one fp32, contiguous, device-resident parameter to the engine under its reference
  * state-dict key (e.g. "input_blocks.1.0.in_layers.2.weight").  The engine copies/repacks
- * it into kernel layout at finalize; the caller keeps ownership of `dev_ptr`. */
+ * it into kernel layout at finalize (the engine keeps private copies of everything it reads later; `dev_ptr` is
+ * not dereferenced after eo_unet_finalize returns); the caller keeps ownership of `dev_ptr`. */
 EO_API int eo_unet_set_weight(eo_unet* u, const char* key, const float* dev_ptr,
                        const int64_t* shape, int ndim);
 
@@ -114,6 +115,17 @@ EO_API int eo_unet_finalize(eo_unet* u, int mode, int max_batch, int H, int W, v
 EO_API int eo_unet_forward(eo_unet* u, const float* x, int Cx, const float* cond, int Cc,
                     const int64_t* timesteps, const int64_t* y, float* eps_out, int B,
                     void* stream);
+
+/* Hoist the timestep-embedding path out of the sampling loop (timestep_embedding -> time_embed MLP -> every
+ * ResBlock's emb_layers projection; unet_openai.py:763, :374-376 -- work that depends on the timestep VALUE only):
+ * computes the rows of the timestep values 0 .. n_timesteps-1 once, with the kernels of the per-step path (rows are
+ * bit-identical to it).  While a table is installed, eo_unet_forward with y == NULL gathers row timesteps[b] (one launch
+ * instead of four); a timestep outside [0, n_timesteps) then yields NaN eps, so a sampler installs the table of ITS
+ * schedule (EODiffusion: n_timesteps = self.timesteps) and clears it afterwards.  Class-conditional forwards
+ * (y != NULL) keep the per-step path: label_emb(y) enters before the projections (:764-766).  A table dies with the
+ * plan (eo_unet_finalize).  Synchronises `stream` once. */
+EO_API int eo_unet_build_time_tables(eo_unet* u, int n_timesteps, void* stream);
+EO_API int eo_unet_clear_time_tables(eo_unet* u);
 
 /* Profiling variant of eo_unet_forward used by bench.py's roofline leg: brackets every op of
  * the launch plan with CUDA events on `stream`, waits for the last one and writes the device
@@ -161,7 +173,10 @@ EO_API int64_t eo_unet_read_activation(eo_unet* u, const char* name, float* out_
 #define EO_COEF_EPS_NOCLIP 9        /* (1-alpha[t])/sqrt_one_minus_acp[t]            */
 
 /* x_out = mask*(sa[t]*gt + sb[t]*noise) + (1-mask)*x_t     (model.py:59-60)
- *   x_t, gt, noise, x_out [B,C,H,W]; mask [B,1,H,W]; x_out may alias x_t */
+ *   x_t, gt, noise, x_out [B,C,H,W]; mask [B,1,H,W].
+ * In this and the two step calls below x_out may be the same buffer as x_t (the kernels read and write element i
+ * only, and do not declare the two pointers __restrict__); no other pair of arguments may overlap.  timesteps[b]
+ * must lie in [0, T) of `table` (not checked on the device; the reference's gather would raise). */
 EO_API int eo_ddpm_sum_mix(const float* x_t, const float* gt, const float* mask, const float* noise,
                     const int64_t* timesteps, const float* table, float* x_out, int B, int C,
                     int HW, void* stream);
@@ -192,7 +207,11 @@ EO_API int eo_ddpm_step_mix(const float* x_t, const float* eps, const float* noi
  *   timestep_rows [T][B] int64, row i = the value i repeated (what the reference builds with torch.tensor([i] * n))
  *   table         [T][EO_DDPM_NCOEF], see above
  *   eps_scratch   [B, out_channels, H, W] work buffer for the UNet output
- * Same kernels in the same order as the per-step entry points: bit-identical to driving them from the host. */
+ * Same kernels in the same order as the per-step entry points: bit-identical to driving them from the host.
+ * B, Cx, H, W must match the finalized geometry (batch <= max_batch); installs the timestep tables of 0 .. T-1
+ * (eo_unet_build_time_tables) when y == NULL.
+ * Threading: an eo_unet handle carries per-forward state (staging buffers, CUDA graphs); calls on ONE handle
+ * must be serialised by the caller -- use one handle per host thread / device. */
 EO_API int eo_sample_ddpm(eo_unet* u, float* x, const float* noise_tape, const float* gt, const float* mask,
                    const float* cond, int Cc, const int64_t* y, const int64_t* timestep_rows,
                    const float* table, float* eps_scratch, int T, int B, int Cx, int H, int W, int clip,

@@ -429,10 +429,16 @@ def ddim_step(tab: dict, index: int, x: Tensor, e_t: Tensor, noise: Optional[Ten
 def ddim_sample(sd: dict, cfg: dict, s: dict, S: int, x_T: Tensor,
                 noise_tape: Optional[Sequence[Tensor]] = None, eta: float = 0.,
                 cond: Optional[Tensor] = None, temperature: float = 1.,
-                log_every_t: int = 100, record: Optional[list] = None, eps_fn=None):
+                log_every_t: int = 100, record: Optional[list] = None, eps_fn=None,
+                unconditional_guidance_scale: float = 1.,
+                unconditional_conditioning: Optional[Tensor] = None):
     """DDIMSampler.sample / ddim_sampling (ddim.py:57-164), mask branch excluded (broken
-    in the reference, F7), CFG excluded.  `noise_tape[i]` is the `noise_like` draw of
-    loop iteration i (the `randn_like` at :171 is drawn and discarded by the reference)."""
+    in the reference, F7).  `noise_tape[i]` is the `noise_like` draw of loop iteration i
+    (the `randn_like` at :171 is drawn and discarded by the reference).  With
+    `unconditional_conditioning` and a guidance scale != 1 the classifier-free-guidance
+    branch of p_sample_ddim (:176-181) runs: one UNet call on the doubled batch
+    cat([x, x]), cat([t, t]), cond = cat([unconditional_conditioning, cond]), then
+    e = e_uncond + scale * (e_cond - e_uncond)."""
     T = s["betas"].shape[0]
     ts = ddim_timesteps(S, T)
     tab = ddim_tables(s["alphas_cumprod"], ts, eta)
@@ -443,7 +449,14 @@ def ddim_sample(sd: dict, cfg: dict, s: dict, S: int, x_T: Tensor,
     for i, step in enumerate(np.flip(ts)):
         index = total - i - 1
         t = torch.full((b,), int(step), device=img.device, dtype=torch.long)
-        if eps_fn is not None:
+        cfg_on = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
+        if cfg_on:      # ddim.py:176-181
+            x_in, t_in = torch.cat([img] * 2), torch.cat([t] * 2)
+            c_in = torch.cat([unconditional_conditioning, cond])
+            e_both = eps_fn(x_in, t_in, c_in, None) if eps_fn is not None else unet_forward(sd, cfg, x_in, t_in, cond=c_in)
+            e_u, e_c = e_both.chunk(2)
+            e_t = e_u + unconditional_guidance_scale * (e_c - e_u)
+        elif eps_fn is not None:
             e_t = eps_fn(img, t, cond, None)
         else:
             e_t = unet_forward(sd, cfg, img, t, cond=cond)
