@@ -8,19 +8,26 @@ One "step" = one DDPM reverse step of the whole per-GPU batch: UNet forward (eps
 posterior update + next step's 'sum' conditioning mix.  images/sec = images in flight /
 (T x seconds per step), T = 1000.  Prints ONE JSON line (rank 0).
 
-  value        steps timed on the device with every input resident in HBM
-  e2e          the same step driven through the public drop-in API (EODiffusion methods ->
-               C ABI) from pinned HOST buffers, H2D/D2H copies inside the timed region
-  roofline     the dominant kernel family (tcgen05 implicit-GEMM conv), timed live with CUDA
-               events per op (eo_unet_forward_timed) against MEASURED_PEAKS.json
-  cpu_baseline the CPU oracle (port of the reference path) on the host cores, bounded sample
+  value        steps timed on the device (CUDA events) with every input resident in HBM
+  e2e          the reference's own call, `EODiffusion.sampling(n, device=..., cond=<host tensor>)` followed by
+               `.cpu()`, on a short-T instance of the same model (the UNet cost per step does not depend on T):
+               host RNG draw of x_T, host -> device copies of x_T and cond, every per-step launch of the public
+               loop and the device -> host read of the result are inside the timed region
+  e2e_streamed the per-step entry points (public methods) fed from pinned host buffers with the copies of step
+               k+1 overlapping the compute of step k (what a streaming caller can reach)
+  roofline     the dominant kernel family (tcgen05 implicit-GEMM conv), timed live with CUDA events per op
+               (eo_unet_forward_timed) against MEASURED_PEAKS.json; `achieved` counts ALGORITHMIC FLOPs
+               (SURVEY.md 8d), `achieved_executed` what the launches execute (padded rows, 4/9 sub-pixel form)
+  secondary    the other BASELINE.json configurations (c1, c2, c4, c5), a few device-timed steps each
+  cpu_baseline the reference's CPU path on the host cores, bounded sample (oracle/_ref = the reference's own
+               classes when staged, else the oracle port)
 
-`--impl reference` times the reference's CPU implementation of the path (the oracle port: the
-reference is pure Python/PyTorch and /root/reference is not present on the GPU box).
+`--impl reference` times the reference's CPU implementation of the path (same sources as cpu_baseline).
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -41,13 +48,13 @@ WORKLOADS = {
     "c1": dict(size=64, batch=1, desc="64x64 batch 1 (reference notebook case)"),
     "c2": dict(size=128, batch=16, desc="128x128 batch 16"),
     "c3": dict(size=256, batch=64, desc="256x256 batch 64 per GPU"),
-    # secondary configurations of BASELINE.json (not the headline line; `--workload c4|c5`)
     "c4": dict(size=256, batch=256, kind="ddim", steps_per_image=50,
                desc="256x256 batch 256 per GPU, DDIM S=50 eta=0 (diffusion/ddim.py)"),
     "c5": dict(size=256, batch=64, kind="concat", cx=13, cc=15,
                desc="256x256 batch 64 per GPU, 13-band S2 + 15-channel conditioning concatenated (28 -> 13 ch)"),
 }
 METRIC = "ddpm_T1000_cloud_removal_images_per_sec"
+UNIT = "images/s"
 
 
 def log(*a):
@@ -132,9 +139,10 @@ def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return dict(tflops=float(p["bf16_tflops_sustained"]), gbs=float(p["hbm_gbs"]), src="measured")
+        return dict(tflops=float(p["bf16_tflops_sustained"]), burst=float(p["bf16_tflops"]), gbs=float(p["hbm_gbs"]),
+                    src="measured")
     except Exception:
-        return dict(tflops=1590.0, gbs=6650.0, src="fallback")   # B200_PROFILING.md fallback (burst)
+        return dict(tflops=1590.0, burst=1590.0, gbs=6650.0, src="fallback")   # B200_PROFILING.md fallback (burst)
 
 
 def ncu_traffic(kernel, workload, batch):
@@ -154,20 +162,40 @@ def ncu_traffic(kernel, workload, batch):
 
 
 # ----------------------------------------------------------------------------------------
-# CPU legs (the oracle port of the reference path): cpu_baseline and --impl reference
+# CPU legs: cpu_baseline and --impl reference
 # ----------------------------------------------------------------------------------------
 def cpu_reference_steps(size, batch, steps, warmup):
-    """Time `steps` sampler steps ('sum' mix + UNet + clipped posterior) of the oracle on the host
-    cores.  Returns seconds per step."""
-    from oracle import oracle as O          # test infrastructure: allowed in the CPU legs only
-    from eo_diffusion_b200 import UNetModel
+    """Seconds per sampler step ('sum' mix + UNet + clipped posterior) of the reference's CPU path on all host
+    cores, and which implementation ran: the reference's own classes staged under oracle/_ref ("reference"),
+    else the oracle restatement ("port").  The reference is driven through its public call,
+    EODiffusion.sampling(n, cond=...), on a (warmup + steps)-step instance; step times are the intervals between
+    consecutive UNet calls (forward pre-hook), the last one closed by the call's return."""
     torch.set_num_threads(os.cpu_count() or 1)
+    from oracle import build_ref                 # test infrastructure: allowed in the CPU legs only
+    ref = build_ref.import_reference()
+    host, _ = synth_inputs(batch, size, 0, "cpu")
+    cond = torch.cat([host["gt"], host["mask"]], 1)
+    if ref is not None:
+        RefDiffusion, RefUNet, _, ref_mod = ref
+        torch.manual_seed(1234)
+        unet = randomize_zero_init_(RefUNet(image_size=size, **ARCH)).eval()
+        diff = RefDiffusion(unet, size, 3, timesteps=warmup + steps, cond_type="sum").eval()
+        ref_mod.save_image = lambda *a, **k: None        # sampling() writes PNGs unconditionally (SURVEY.md F3)
+        stamps = []
+        h = unet.register_forward_pre_hook(lambda m, a: stamps.append(time.perf_counter()))
+        with torch.no_grad():
+            diff.sampling(batch, clipped_reverse_diffusion=True, device="cpu", cond=cond)
+        stamps.append(time.perf_counter())
+        h.remove()
+        dt = [b - a for a, b in zip(stamps[:-1], stamps[1:])][warmup:]
+        return sum(dt) / len(dt), "reference"
+    from oracle import oracle as O
+    from eo_diffusion_b200 import UNetModel
     torch.manual_seed(1234)
     m = randomize_zero_init_(UNetModel(image_size=size, **ARCH))
     sd = {k: v.detach() for k, v in m.state_dict().items()}
     cfg = O.full_cfg(image_size=size, **ARCH)
     s = O.cosine_schedule(T_DDPM)
-    host, _ = synth_inputs(batch, size, 0, "cpu")
     x, gt, mask = host["x"], host["gt"], host["mask"]
     times = []
     with torch.no_grad():
@@ -180,7 +208,7 @@ def cpu_reference_steps(size, batch, steps, warmup):
             x = O.reverse_step_clip(s, x, t, nz, eps)
             if k >= warmup:
                 times.append(time.perf_counter() - t0)
-    return sum(times) / len(times)
+    return sum(times) / len(times), "port"
 
 
 def run_reference(args, wl):
@@ -189,18 +217,20 @@ def run_reference(args, wl):
         return
     size = wl["size"]
     sample_b = 1
-    sec = cpu_reference_steps(size, sample_b, args.steps, args.warmup)
+    sec, kind = cpu_reference_steps(size, sample_b, args.steps, args.warmup)
     val = sample_b / (T_DDPM * sec)
     cores = torch.get_num_threads()
-    sample = f"{sample_b} image(s) of {size}x{size}, {args.steps} sampler steps (of T={T_DDPM}) after {args.warmup} warm-up"
+    sample = (f"{sample_b} image(s) of {size}x{size}, {args.steps} sampler steps (of T={T_DDPM}) after {args.warmup} "
+              f"warm-up, " + ("the reference's own EODiffusion.sampling + UNetModel (oracle/_ref)" if kind == "reference"
+                              else "oracle restatement of the reference path"))
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}, DDPM T={T_DDPM}, cond 'sum', clipped; "
                                f"CPU arm runs a bounded sample: {sample}"},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
 
@@ -208,110 +238,170 @@ def run_reference(args, wl):
 # ----------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------
-def run_ours(args, wl):
-    import ctypes as C
-    from eo_diffusion_b200 import EODiffusion, UNetModel, _lib
+class Ctx:
+    """One workload on one rank: the model, its inputs and the per-step driver."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    L = _lib.lib()
-    _lib.check(L.eo_device_check(), "eo_device_check")
+    def __init__(self, name, wl, batch, mode, dev, rank):
+        import ctypes as C
+        from eo_diffusion_b200 import EODiffusion, UNetModel, _lib
+        self.C, self.lib, self.L = C, _lib, _lib.lib()
+        self.name, self.wl, self.dev, self.mode = name, wl, dev, mode
+        self.size, self.B = wl["size"], batch
+        self.kind = wl.get("kind", "sum")
+        self.steps_per_image = wl.get("steps_per_image", T_DDPM)
+        self.cx, self.cc = wl.get("cx", 3), wl.get("cc", 0)
+        arch = dict(ARCH, in_channels=self.cx + self.cc, out_channels=self.cx)
+        torch.manual_seed(1234)
+        self.model = randomize_zero_init_(UNetModel(image_size=self.size, **arch)).to(dev).set_compute_mode(mode)
+        self.diff = EODiffusion(self.model, self.size, self.cx, timesteps=T_DDPM,
+                                cond_type="sum" if self.kind == "sum" else None).to(dev)
+        self.host, self.d = synth_inputs(batch, self.size, 100 + rank, dev, pin=True, channels=self.cx,
+                                         cond_channels=self.cc)
+        self.tab = self.diff._coef_table(dev)
+        self.ts_rows = self.diff._timestep_rows(batch, dev)
+        self.hw = self.size * self.size
+        self.nz = [self.d["nz0"], self.d["nz1"]]
+        self.x = self.d["x"].clone()
+        self.sampler = None
+        if self.kind == "ddim":
+            from eo_diffusion_b200 import DDIMSampler
+            self.sampler = DDIMSampler(self.diff)
+            self.sampler.make_schedule(ddim_num_steps=self.steps_per_image, ddim_eta=0.0, verbose=False)
+            self.ddim_ts = [int(v) for v in self.sampler.ddim_timesteps]
+            self.scal = []
+            for idx in range(len(self.ddim_ts)):       # the scalars DDIMSampler.p_sample_ddim hands to eo_ddim_step
+                a_t, a_prev = float(self.sampler.ddim_alphas[idx]), float(self.sampler.ddim_alphas_prev[idx])
+                sg = float(self.sampler.ddim_sigmas[idx])
+                self.scal.append((math.sqrt(a_t), float(self.sampler.ddim_sqrt_one_minus_alphas[idx]), math.sqrt(a_prev),
+                                  math.sqrt(max(1. - a_prev - sg * sg, 0.)), sg))
+            self.pred_x0 = torch.empty_like(self.x)
 
-    size, B, mode = wl["size"], args.batch or wl["batch"], args.mode
-    kind = wl.get("kind", "sum")
-    steps_per_image = wl.get("steps_per_image", T_DDPM)
-    cx, cc = wl.get("cx", 3), wl.get("cc", 0)
-    arch = dict(ARCH, in_channels=cx + cc, out_channels=cx)
-    torch.manual_seed(1234)
-    model = randomize_zero_init_(UNetModel(image_size=size, **arch)).to(dev).set_compute_mode(mode)
-    diff = EODiffusion(model, size, cx, timesteps=T_DDPM, cond_type="sum" if kind == "sum" else None).to(dev)
-    host, d = synth_inputs(B, size, 100 + rank, dev, pin=True, channels=cx, cond_channels=cc)
-    tab = diff._coef_table(dev)
-    ts_rows = diff._timestep_rows(B, dev)
-    hw = size * size
-    nz = [d["nz0"], d["nz1"]]
-    x = d["x"].clone()
-    stream = _lib.stream_ptr
-    sampler = None
-    if kind == "ddim":
-        from eo_diffusion_b200 import DDIMSampler
-        sampler = DDIMSampler(diff)
-        sampler.make_schedule(ddim_num_steps=steps_per_image, ddim_eta=0.0, verbose=False)
-        ddim_ts = [int(v) for v in sampler.ddim_timesteps]
-        scal = []
-        for idx in range(len(ddim_ts)):            # the scalars DDIMSampler.p_sample_ddim hands to eo_ddim_step
-            a_t, a_prev = float(sampler.ddim_alphas[idx]), float(sampler.ddim_alphas_prev[idx])
-            sg = float(sampler.ddim_sigmas[idx])
-            scal.append((math.sqrt(a_t), float(sampler.ddim_sqrt_one_minus_alphas[idx]), math.sqrt(a_prev),
-                         math.sqrt(max(1. - a_prev - sg * sg, 0.)), sg))
-        pred_x0 = torch.empty_like(x)
+    def close(self):
+        self.model = self.diff = self.sampler = None
+        self.host = self.d = self.x = self.nz = None
+        gc.collect()
+        torch.cuda.empty_cache()
 
-    def device_step(k):
-        if kind == "ddim":
-            idx = len(ddim_ts) - 1 - (k % len(ddim_ts))
-            pred = model(x, ts_rows[ddim_ts[idx]])
-            sa, s1, sp, dc, sg = scal[idx]
-            _lib.check(L.eo_ddim_step(_lib.ptr(x), _lib.ptr(pred), None, _lib.ptr(x), _lib.ptr(pred_x0), sa, s1, sp, dc,
-                                      sg, 1.0, x.numel(), stream()), "eo_ddim_step")
+    def first_mix(self):
+        if self.kind == "sum":
+            p, d = self.lib.ptr, self.d
+            self.lib.check(self.L.eo_ddpm_sum_mix(p(self.x), p(d["gt"]), p(d["mask"]), p(self.nz[0]),
+                                                  p(self.ts_rows[T_DDPM - 1]), p(self.tab), p(self.x), self.B, 3, self.hw,
+                                                  self.lib.stream_ptr()))
+
+    def device_step(self, k):
+        """One sampler step with every operand resident in HBM (the timestep tables of the schedule installed, as
+        EODiffusion.sampling / DDIMSampler.sample do for their loops)."""
+        p, L, d, x, B = self.lib.ptr, self.L, self.d, self.x, self.B
+        st = self.lib.stream_ptr
+        if self.kind == "ddim":
+            idx = len(self.ddim_ts) - 1 - (k % len(self.ddim_ts))
+            pred = self.model(x, self.ts_rows[self.ddim_ts[idx]])
+            sa, s1, sp, dc, sg = self.scal[idx]
+            self.lib.check(L.eo_ddim_step(p(x), p(pred), None, p(x), p(self.pred_x0), sa, s1, sp, dc, sg, 1.0, x.numel(),
+                                          st()), "eo_ddim_step")
             return
         i = T_DDPM - 1 - (k % (T_DDPM - 1))           # i >= 1
-        if kind == "concat":
-            pred = model(x, ts_rows[i], cond=d["cond"])
-            _lib.check(L.eo_ddpm_step(_lib.ptr(x), _lib.ptr(pred), _lib.ptr(nz[k % 2]), _lib.ptr(ts_rows[i]), _lib.ptr(tab),
-                                      _lib.ptr(x), B, cx, hw, 1, 1, stream()), "eo_ddpm_step")
+        t = self.ts_rows[i]
+        if self.kind == "concat":
+            pred = self.model(x, t, cond=d["cond"])
+            self.lib.check(L.eo_ddpm_step(p(x), p(pred), p(self.nz[k % 2]), p(t), p(self.tab), p(x), B, self.cx, self.hw,
+                                          1, 1, st()), "eo_ddpm_step")
             return
-        pred = model(x, ts_rows[i])
-        _lib.check(L.eo_ddpm_step_mix(_lib.ptr(x), _lib.ptr(pred), _lib.ptr(nz[k % 2]), _lib.ptr(ts_rows[i]),
-                                      _lib.ptr(d["gt"]), _lib.ptr(d["mask"]), _lib.ptr(nz[(k + 1) % 2]),
-                                      _lib.ptr(ts_rows[i - 1]), _lib.ptr(tab), _lib.ptr(x), B, 3, hw, 1, 1,
-                                      stream()), "eo_ddpm_step_mix")
+        pred = self.model(x, t)
+        self.lib.check(L.eo_ddpm_step_mix(p(x), p(pred), p(self.nz[k % 2]), p(t), p(d["gt"]), p(d["mask"]),
+                                          p(self.nz[(k + 1) % 2]), p(self.ts_rows[i - 1]), p(self.tab), p(x), B, 3,
+                                          self.hw, 1, 1, st()), "eo_ddpm_step_mix")
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
+    def time_device_steps(self, steps, warmup, barrier, clocks=None):
+        self.first_mix()
+        with self.model.time_tables(T_DDPM + 1):
+            for k in range(warmup):
+                self.device_step(k)
+            barrier()
+            if clocks is not None:
+                clocks.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(steps):
+                self.device_step(warmup + k)
+            e1.record()
+            barrier()
+            launches = self.model.launches_per_forward() + 1
+        assert bool(torch.isfinite(self.x).all()), "sampler state diverged"
+        return e0.elapsed_time(e1) / steps, launches
+
+    def op_table(self):
+        """Per-op CUDA-event times of one warm UNet forward + the engine's FLOP notes."""
+        C, L, lib = self.C, self.L, self.lib
+        h = C.c_void_p(self.model._handle)
+        nops = L.eo_unet_num_ops(h)
+        ms = (C.c_float * nops)()
+        eps = torch.empty((self.B, self.cx, self.size, self.size), device=self.dev)
+        cond_p = lib.ptr(self.d["cond"]) if self.kind == "concat" else None
+        for _ in range(2):   # second pass is the warm one
+            lib.check(L.eo_unet_forward_timed(h, lib.ptr(self.x), self.cx, cond_p, self.cc, lib.ptr(self.ts_rows[500]),
+                                              None, lib.ptr(eps), self.B, lib.stream_ptr(), ms), "eo_unet_forward_timed")
+        name, kern, fl, by = C.c_char_p(), C.c_char_p(), C.c_double(), C.c_double()
+        ops = []
+        for i in range(nops):
+            L.eo_unet_op_info(h, i, C.byref(name), C.byref(kern), C.byref(fl), C.byref(by))
+            ops.append(dict(name=name.value.decode(), kernel=kern.value.decode(), ms=ms[i], flops=fl.value * self.B,
+                            exec_flops=L.eo_unet_op_executed_flops(h, i) * self.B, bytes=by.value * self.B))
+        return ops
+
+    def alg_flops_per_image(self):
+        C, L = self.C, self.L
+        h = C.c_void_p(self.model._handle)
+        fl = C.c_double()
+        tot = 0.0
+        for i in range(L.eo_unet_num_ops(h)):
+            L.eo_unet_op_info(h, i, None, None, C.byref(fl), None)
+            tot += fl.value
+        return tot
+
+
+def e2e_public_sampling(ctx, steps, barrier):
+    """The reference's call (inference.py:121-126): EODiffusion.sampling(n, device=..., cond=<host tensor>) then the
+    result on the host.  Short-T instance (UNet and step kernels do not depend on T).  Returns (ms per step, h2d, d2h)."""
+    from eo_diffusion_b200 import EODiffusion
+    B, size, dev = ctx.B, ctx.size, ctx.dev
+    if ctx.kind == "sum":
+        cond = torch.cat([ctx.host["gt"], ctx.host["mask"]], 1).pin_memory()
+    elif ctx.kind == "concat":
+        cond = ctx.host["cond"]
+    else:
+        cond = None
+    h2d = B * ctx.cx * size * size * 4 + (cond.numel() * 4 if cond is not None else 0)       # x_T + cond, once per call
+    d2h = B * ctx.cx * size * size * 4
+
+    def call(T):
+        if ctx.kind == "ddim":
+            with torch.no_grad():
+                out, _ = ctx.sampler.sample(T, B, (ctx.cx, size, size), eta=0.0, verbose=False)
+            return out.cpu()
+        diff = EODiffusion(ctx.model, size, ctx.cx, timesteps=T, cond_type="sum" if ctx.kind == "sum" else None).to(dev)
+        return diff.sampling(B, clipped_reverse_diffusion=True, device=dev, cond=cond, write_pngs=False).cpu()
+
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):      # the DDIM sampler prints like the reference does
+        call(3)                                          # warm: plans, graph capture, allocator
+        barrier()
+        t0 = time.perf_counter()
+        out = call(steps)
         torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        import torch.distributed as dist
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident steps ------------------------------------------------------------
-    if kind == "sum":
-        _lib.check(L.eo_ddpm_sum_mix(_lib.ptr(x), _lib.ptr(d["gt"]), _lib.ptr(d["mask"]), _lib.ptr(nz[0]),
-                                     _lib.ptr(ts_rows[T_DDPM - 1]), _lib.ptr(tab), _lib.ptr(x), B, 3, hw, stream()))
-    for k in range(args.warmup):
-        device_step(k)
+        dt = time.perf_counter() - t0
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(args.steps):
-        device_step(args.warmup + k)
-    e1.record()
-    barrier()
-    clk = clocks.finish()
-    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    value = world * B / (steps_per_image * ms_step * 1e-3)
-    assert bool(torch.isfinite(x).all()), "sampler state diverged"
-    launches_step = model.launches_per_forward() + 1
+    assert bool(torch.isfinite(out).all())
+    return dt * 1e3 / steps, h2d / steps, d2h / steps
 
-    # ---- end to end through the public API from pinned host buffers ---------------------------
-    # Every step copies ITS inputs host -> device and its result device -> host inside the timed region.  The copies run
-    # on a side stream into double-buffered device tensors, so step k+1's inputs travel while step k computes (a
-    # sampler's noise / conditioning for the next step do not depend on the current one); the result goes back on a
-    # third stream.  The first step's inputs and the last step's result are not overlapped with anything.
+
+def e2e_streamed(ctx, n_steps, barrier):
+    """Per-step public methods fed from pinned host buffers: every step copies ITS inputs host -> device and its result
+    device -> host inside the timed region, on side streams into double-buffered device tensors, so step k+1's inputs
+    travel while step k computes."""
+    lib, L, d, host, B, kind = ctx.lib, ctx.L, ctx.d, ctx.host, ctx.B, ctx.kind
     hx = host["x"].clone().pin_memory()
     out_host = torch.empty_like(hx).pin_memory()
 
@@ -334,7 +424,7 @@ def run_ours(args, wl):
     main_s = torch.cuda.current_stream()
     in_s, out_s = torch.cuda.Stream(), torch.cuda.Stream()
     ev_in = [torch.cuda.Event(), torch.cuda.Event()]      # slot's inputs have landed
-    ev_free = [torch.cuda.Event(), torch.cuda.Event()]    # the step that read the slot has been enqueued and finished
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]    # the step that read the slot has finished
     ev_done, ev_out = torch.cuda.Event(), torch.cuda.Event()
 
     def stage_inputs(k):
@@ -351,24 +441,24 @@ def run_ours(args, wl):
                 b["cond"].copy_(host["cond"], non_blocking=True)
             ev_in[k % 2].record(in_s)
 
-    def e2e_step(k, last):
+    def step(k, last):
         b = slots[k % 2]
         if not last:
             stage_inputs(k + 1)
         main_s.wait_event(ev_in[k % 2])
         dx, dn = b["x"], b["n"]
         if kind == "ddim":
-            idx = len(ddim_ts) - 1 - (k % len(ddim_ts))
-            nxt, _ = sampler.p_sample_ddim(dx, None, ts_rows[ddim_ts[idx]], index=idx)   # public method: UNet + DDIM update
+            idx = len(ctx.ddim_ts) - 1 - (k % len(ctx.ddim_ts))
+            nxt, _ = ctx.sampler.p_sample_ddim(dx, None, ctx.ts_rows[ctx.ddim_ts[idx]], index=idx)
         else:
             i = T_DDPM - 1 - (k % (T_DDPM - 1))
-            t = ts_rows[i]
+            t = ctx.ts_rows[i]
             if kind == "concat":
-                nxt = diff._reverse_diffusion_with_clip(dx, t, dn, cond=b["cond"])
+                nxt = ctx.diff._reverse_diffusion_with_clip(dx, t, dn, cond=b["cond"])
             else:
-                _lib.check(L.eo_ddpm_sum_mix(_lib.ptr(dx), _lib.ptr(b["gt"]), _lib.ptr(b["m"]), _lib.ptr(dn), _lib.ptr(t),
-                                             _lib.ptr(tab), _lib.ptr(dx), B, 3, hw, stream()))
-                nxt = diff._reverse_diffusion_with_clip(dx, t, dn)      # public method: UNet + posterior
+                lib.check(L.eo_ddpm_sum_mix(lib.ptr(dx), lib.ptr(b["gt"]), lib.ptr(b["m"]), lib.ptr(dn), lib.ptr(t),
+                                            lib.ptr(ctx.tab), lib.ptr(dx), B, 3, ctx.hw, lib.stream_ptr()))
+                nxt = ctx.diff._reverse_diffusion_with_clip(dx, t, dn)
         ev_free[k % 2].record(main_s)
         ev_done.record(main_s)
         main_s.wait_event(ev_out)              # the previous result has left before its buffer can be reused
@@ -378,93 +468,227 @@ def run_ours(args, wl):
             ev_out.record(out_s)
         nxt.record_stream(out_s)
 
-    n_e2e = max(2, args.steps)
     for ev in ev_free:
         ev.record(main_s)
     ev_out.record(out_s)
-    stage_inputs(0)
-    e2e_step(0, True)
-    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ctx.model.time_tables(T_DDPM + 1):
+        stage_inputs(0)
+        step(0, True)
+        barrier()
+        e0.record()
+        stage_inputs(1)
+        for k in range(n_steps):
+            step(k + 1, k == n_steps - 1)
+        main_s.wait_event(ev_out)                  # the last result is on the host
+        e1.record()
+        barrier()
+    return e0.elapsed_time(e1) / n_steps, h2d, d2h
+
+
+def sharded_equals_single(ctx, rank, world):
+    """Multi-GPU evidence the line can carry: three sampler steps of a small global batch through the
+    whole-loop C entry point, each rank its contiguous slice of ONE shared noise tape; the NCCL all-gather of the
+    slices must equal, bit for bit, rank 0's own run of the whole batch.  Returns (ok, collective ms of the bench-size
+    gather)."""
+    import torch.distributed as dist
+    lib, L, C = ctx.lib, ctx.L, ctx.C
+    dev, size, cx = ctx.dev, ctx.size, ctx.cx
+    per, T = 2, 3
+    n = per * world
+    g = torch.Generator().manual_seed(4242)
+    x_T = torch.randn((n, cx, size, size), generator=g)
+    tape = torch.randn((T, n, cx, size, size), generator=g)
+    gt = torch.rand((n, 3, size, size), generator=g)
+    mask = (torch.rand((n, 1, size, size), generator=g) > 0.3).float()
+    cond = torch.rand((n, max(ctx.cc, 1), size, size), generator=g)
+    from eo_diffusion_b200 import EODiffusion
+    diff = EODiffusion(ctx.model, size, cx, timesteps=T, cond_type="sum" if ctx.kind == "sum" else None).to(dev)
+    tab = diff._coef_table(dev)
+
+    def run(lo, hi):
+        b = hi - lo
+        x = x_T[lo:hi].contiguous().to(dev)
+        tp = tape[:, lo:hi].contiguous().to(dev)
+        rows = diff._timestep_rows(b, dev)
+        eps = torch.empty_like(x)
+        sum_mode = ctx.kind == "sum"
+        g_, m_ = (gt[lo:hi].contiguous().to(dev), mask[lo:hi].contiguous().to(dev)) if sum_mode else (None, None)
+        c_ = cond[lo:hi, :ctx.cc].contiguous().to(dev) if ctx.cc else None
+        ctx.model(x, rows[0], cond=c_)      # plan for this batch size
+        lib.check(L.eo_sample_ddpm(C.c_void_p(ctx.model._handle), lib.ptr(x), lib.ptr(tp), lib.ptr(g_), lib.ptr(m_),
+                                   lib.ptr(c_), ctx.cc, None, lib.ptr(rows), lib.ptr(tab), lib.ptr(eps), T, b, cx, size,
+                                   size, 1, lib.stream_ptr()), "eo_sample_ddpm")
+        return x
+
+    mine = run(rank * per, (rank + 1) * per)
+    gathered = torch.empty((n, cx, size, size), device=dev)
+    dist.all_gather_into_tensor(gathered, mine)
+    ok = torch.ones((1,), device=dev)
+    if rank == 0:
+        whole = run(0, n)
+        ok[0] = 1.0 if torch.equal(whole, gathered) else 0.0
+    dist.broadcast(ok, 0)
+    # the one collective of the path at bench size: gather the final images of all ranks
+    big = torch.empty((world * ctx.B, cx, size, size), device=dev)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    stage_inputs(1)
-    for k in range(n_e2e):
-        e2e_step(k + 1, k == n_e2e - 1)
-    main_s.wait_event(ev_out)                  # the last result is on the host
+    dist.all_gather_into_tensor(big, ctx.x)
     e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / n_e2e)
-    e2e_value = world * B / (steps_per_image * ms_e2e * 1e-3)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(ok.item() == 1.0), float(t.item())
+
+
+def run_ours(args, wl):
+    from eo_diffusion_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.check(_lib.lib().eo_device_check(), "eo_device_check")
+    mode = args.mode
+    peaks = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B = args.batch or wl["batch"]
+    ctx = Ctx(args.workload, wl, B, mode, dev, rank)
+    size, kind, steps_per_image = ctx.size, ctx.kind, ctx.steps_per_image
+
+    # ---- device-resident steps ------------------------------------------------------------
+    clocks = ClockSampler(local)
+    ms_local, launches_step = ctx.time_device_steps(args.steps, args.warmup, barrier, clocks)
+    clk = clocks.finish()
+    ms_step = max_over_ranks(ms_local)
+    value = world * B / (steps_per_image * ms_step * 1e-3)
+
+    # ---- end to end ---------------------------------------------------------------------------
+    n_e2e = max(args.steps, 50 if B * size * size <= 64 * 256 * 256 else 10)
+    if kind == "ddim":
+        n_e2e = steps_per_image
+    ms_pub, h2d_pub, d2h_pub = e2e_public_sampling(ctx, n_e2e, barrier)
+    ms_pub = max_over_ranks(ms_pub)
+    e2e_value = world * B / (steps_per_image * ms_pub * 1e-3)
+    ms_str, h2d_str, d2h_str = e2e_streamed(ctx, max(2, args.steps), barrier)
+    ms_str = max_over_ranks(ms_str)
 
     # ---- roofline of the dominant kernel family, timed per op with CUDA events --------------
     roofline = None
-    breakdown = {}
+    flops_img = None
+    attention = None
     if rank == 0:
-        h = C.c_void_p(model._handle)
-        nops = L.eo_unet_num_ops(h)
-        ms = (C.c_float * nops)()
-        eps = torch.empty((B, cx, size, size), device=dev)
-        cond_p = _lib.ptr(d["cond"]) if kind == "concat" else None
-        for _ in range(2):   # second pass is the warm one
-            _lib.check(L.eo_unet_forward_timed(h, _lib.ptr(x), cx, cond_p, cc, _lib.ptr(ts_rows[500]), None,
-                                               _lib.ptr(eps), B, stream(), ms), "eo_unet_forward_timed")
-        name, kern, fl, by = C.c_char_p(), C.c_char_p(), C.c_double(), C.c_double()
-        for i in range(nops):
-            L.eo_unet_op_info(h, i, C.byref(name), C.byref(kern), C.byref(fl), C.byref(by))
-            e = breakdown.setdefault(kern.value.decode(), dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
-            e["ms"] += ms[i]
-            e["flops"] += fl.value * B
-            e["bytes"] += by.value * B
+        ops = ctx.op_table()
+        breakdown = {}
+        for o in ops:
+            e = breakdown.setdefault(o["kernel"], dict(ms=0.0, flops=0.0, exec_flops=0.0, bytes=0.0, launches=0))
+            e["ms"] += o["ms"]; e["flops"] += o["flops"]; e["exec_flops"] += o["exec_flops"]; e["bytes"] += o["bytes"]
             e["launches"] += 1
-        peaks = measured_peaks()
-        fam = next(k for k in ("k_conv_tc3", "k_conv_tc", "k_conv_simt") if k in breakdown)
+        fam = next(k for k in ("k_conv_tc3", "k_conv_simt") if k in breakdown)
         e = breakdown[fam]
         ach = e["flops"] / (e["ms"] * 1e-3) / 1e12
+        ach_x = e["exec_flops"] / (e["ms"] * 1e-3) / 1e12
         total_ms = sum(v["ms"] for v in breakdown.values())
+        total_fl = sum(v["flops"] for v in breakdown.values())
+        flops_img = total_fl / B
         roofline = {"bound": "tensor", "kernel": fam, "achieved": ach, "peak": peaks["tflops"],
                     "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": ncu_traffic(fam, args.workload, B),
-                    "peak_source": f"{peaks['src']} bf16_tflops_sustained",
+                    "achieved_executed": ach_x, "frac_executed": ach_x / peaks["tflops"],
+                    "peak_source": f"{peaks['src']} bf16_tflops_sustained (burst {peaks['burst']})",
                     "flops_per_launch_avg": e["flops"] / e["launches"], "launches_per_step": e["launches"],
-                    "share_of_unet_time": e["ms"] / total_ms}
+                    "share_of_unet_time": e["ms"] / total_ms,
+                    "whole_step": {"achieved": total_fl / (ms_step * 1e-3) / 1e12,
+                                   "frac": total_fl / (ms_step * 1e-3) / 1e12 / peaks["tflops"]}}
+        a = breakdown.get("k_attn_tc5")
+        if a:
+            attention = {"ms": a["ms"], "share_of_unet_time": a["ms"] / total_ms,
+                         "achieved": a["flops"] / (a["ms"] * 1e-3) / 1e12,
+                         "achieved_executed": a["exec_flops"] / (a["ms"] * 1e-3) / 1e12, "unit": "TFLOP/s",
+                         "bound": "mufu+issue (one ex2 per logit; DESIGN.md section 4)"}
         log("[bench] per-kernel-family breakdown of one UNet forward (CUDA events per op):")
         for kname, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"]):
             extra = ""
             if v["flops"]:
-                extra = f"{v['flops'] / (v['ms'] * 1e-3) / 1e12:8.1f} TFLOP/s"
+                extra = (f"{v['flops'] / (v['ms'] * 1e-3) / 1e12:8.1f} TFLOP/s algorithmic "
+                         f"{v['exec_flops'] / (v['ms'] * 1e-3) / 1e12:8.1f} executed")
             elif v["bytes"]:
                 extra = f"{v['bytes'] / (v['ms'] * 1e-3) / 1e9:8.1f} GB/s"
             log(f"    {kname:18s} {v['ms']:9.3f} ms  {100 * v['ms'] / total_ms:5.1f}%  x{v['launches']:3d}  {extra}")
         if args.breakdown:
-            ops = []
-            for i in range(nops):
-                L.eo_unet_op_info(h, i, C.byref(name), C.byref(kern), C.byref(fl), C.byref(by))
-                ops.append(dict(name=name.value.decode(), kernel=kern.value.decode(), ms=ms[i],
-                                flops=fl.value * B, bytes=by.value * B))
             with open(args.breakdown, "w") as f:
                 json.dump(dict(workload=args.workload, batch=B, size=size, mode=mode, ops=ops), f, indent=1)
+
+    # ---- multi-GPU: bit-equality of the sharded run + the one collective -----------------------
+    multi = None
+    if world > 1:
+        ok, coll_ms = sharded_equals_single(ctx, rank, world)
+        multi = {"sharded_equals_single": ok, "collective_ms": coll_ms,
+                 "collective": "all_gather_into_tensor of the final images, once per trajectory (outside the timed steps)"}
+    ctx.close()
+
+    # ---- the other BASELINE.json configurations, a few device-timed steps each -----------------
+    secondary = None
+    if not args.no_secondary and args.workload == "c3" and not args.batch:
+        secondary = {}
+        names = ["c1", "c2", "c4", "c5"] if world == 1 else ["c5"]
+        for name in names:
+            w2 = WORKLOADS[name]
+            try:
+                c2 = Ctx(name, w2, w2["batch"], mode, dev, rank)
+                k2 = 20 if name in ("c1", "c2") else 3
+                ms2, l2 = c2.time_device_steps(k2, 3, barrier)
+                ms2 = max_over_ranks(ms2)
+                fl2 = c2.alg_flops_per_image()
+                spi = c2.steps_per_image
+                secondary[name] = {"workload": w2["desc"], "value": world * w2["batch"] / (spi * ms2 * 1e-3), "unit": UNIT,
+                                   "steps_per_image": spi, "ms_per_step": ms2, "steps": k2, "batch_per_gpu": w2["batch"],
+                                   "frac": fl2 * w2["batch"] / (ms2 * 1e-3) / 1e12 / peaks["tflops"],
+                                   "gpu_launches_per_step": l2}
+                c2.close()
+            except Exception as ex:      # a secondary line must not cost the headline
+                secondary[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+                gc.collect()
+                torch.cuda.empty_cache()
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and kind == "sum":
         sample_b, sample_steps = 1, 10        # ~1 s per step on 16 host threads: 10-12 s of CPU work
-        sec = cpu_reference_steps(size, sample_b, sample_steps, 1)
-        cpu = {"value": sample_b / (T_DDPM * sec), "unit": "images/s", "cores": torch.get_num_threads(),
-               "kind": "port", "ms_per_step": sec * 1e3,
-               "sample": f"{sample_b} image of {size}x{size}, {sample_steps} sampler steps after 1 warm-up "
-                         f"(oracle port of the reference CPU path, fp32)"}
+        sec, ckind = cpu_reference_steps(size, sample_b, sample_steps, 1)
+        cpu = {"value": sample_b / (T_DDPM * sec), "unit": UNIT, "cores": torch.get_num_threads(),
+               "kind": ckind, "ms_per_step": sec * 1e3,
+               "sample": f"{sample_b} image of {size}x{size}, {sample_steps} sampler steps after 1 warm-up ("
+                         + ("the reference's own EODiffusion.sampling + UNetModel from oracle/_ref"
+                            if ckind == "reference" else "oracle port of the reference CPU path") + ", fp32)"}
 
     if world > 1:
-        # the one collective of the path: gather the final images of all ranks
         import torch.distributed as dist
-        gathered = torch.empty((world * B, cx, size, size), device=dev)
-        dist.all_gather_into_tensor(gathered, x)
-        torch.cuda.synchronize()
         dist.destroy_process_group()
 
     if rank == 0:
-        flops_img = sum(v["flops"] for v in breakdown.values()) / B if breakdown else None
         print(json.dumps({
             "metric": METRIC if kind != "ddim" else f"ddim_S{steps_per_image}_images_per_sec", "value": value,
-            "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": mode, "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}, "
@@ -476,12 +700,20 @@ def run_ours(args, wl):
                        "l2": "activations per step (GBs) exceed the 126 MB L2; no flush needed"
                              if B * size * size * 128 * 2 > 4 * 126e6 else
                              "working set fits L2: numbers are L2-warm"},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e, "steps": n_e2e},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_pub, "d2h_bytes_per_step": d2h_pub,
+                    "ms_per_step": ms_pub, "steps": n_e2e,
+                    "call": "EODiffusion.sampling(n, device, cond=<pinned host tensor>).cpu() on a "
+                            f"{n_e2e}-step instance; x_T drawn on the host like the reference; copies once per call, "
+                            "divided over its steps" if kind != "ddim" else "DDIMSampler.sample(S, ...)[0].cpu()"},
+            "e2e_streamed": {"value": world * B / (steps_per_image * ms_str * 1e-3), "unit": UNIT,
+                             "h2d_bytes_per_step": h2d_str, "d2h_bytes_per_step": d2h_str, "ms_per_step": ms_str},
             "gpu_launches": launches_step * args.steps,
             "clocks": clk,
             "roofline": roofline,
+            "attention": attention,
             "unet_algorithmic_gflop_per_image_step": flops_img / 1e9 if flops_img else None,
+            "multi_gpu": multi,
+            "secondary": secondary,
             "cpu_baseline": cpu,
         }), flush=True)
 
@@ -497,6 +729,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--breakdown", default="", help="write the per-op timing JSON here")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the c1/c2/c4/c5 block of the default line")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                    # timing rule: at least 3 warm-up steps

@@ -57,6 +57,7 @@ SIGNATURES = {
     "eo_unet_num_ops": (_I, [_P]),
     "eo_unet_op_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
                              C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "eo_unet_op_executed_flops": (C.c_double, [_P, _I]),
     "eo_unet_device_bytes": (_L, [_P]),
     "eo_unet_launches_per_forward": (_I, [_P]),
     "eo_unet_read_activation": (_L, [_P, C.c_char_p, _P, _L, _I, _P]),

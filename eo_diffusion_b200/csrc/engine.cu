@@ -102,6 +102,7 @@ struct Op {
   std::function<int(int, cudaStream_t)> run;           // (B, stream)
   const char* kernel = "";                             // kernel family (for bench.py's roofline)
   double flops = 0;                                    // algorithmic FLOPs per image
+  double exec_flops = 0;                               // FLOPs the launch executes per image (padded rows, folded taps)
   double bytes = 0;                                    // algorithmic HBM bytes per image
 };
 
@@ -141,10 +142,11 @@ struct eo_unet {
   // computed once per sampling loop instead of once per step (unet_openai.py:763, :374-376)
   float* tt_table = nullptr;
   int tt_n = 0;
+  bool tt_on = false;               // forwards gather from the table (set by build, cleared by clear / finalize; the
+                                    // whole-loop entry points switch it on for their own loop only)
   void release_time_tables() {
     if (tt_table) { cudaFree(tt_table); dev_bytes -= (int64_t)tt_n * tb_total * sizeof(float); }
-    tt_table = nullptr; tt_n = 0;
-    release_graphs_only();          // captured graphs contain the other variant of the time_embed op
+    tt_table = nullptr; tt_n = 0; tt_on = false;
   }
   int build_time_tables(int n, cudaStream_t st);
   double* ch_stats = nullptr;       // per-channel GroupNorm sums emitted by conv epilogues (zeroed per forward)
@@ -381,8 +383,9 @@ struct eo_unet {
     n_launches += launches;
   }
   // annotate the op pushed last
-  void note(const char* kernel, double flops, double bytes) {
+  void note(const char* kernel, double flops, double bytes, double exec_flops = -1.0) {
     ops.back().kernel = kernel; ops.back().flops = flops; ops.back().bytes = bytes;
+    ops.back().exec_flops = exec_flops >= 0 ? exec_flops : flops;
   }
 
   // GroupNorm statistics of (a [, b]) -> scale/shift [Bmax, Ctot] scratch in the arena
@@ -574,8 +577,11 @@ struct eo_unet {
     };
     push(name, [=](int B, cudaStream_t stx) -> int { return tc_conv_launch(tc_plans[plan_idx], B, stx, nchw_C ? io_out : nullptr); },
          1, prepare);
+    // algorithmic FLOPs (2 * out_elems * Cin * k of the reference's layer) next to what the launch
+    // executes (padded qkv / head / stem rows, the 4/9 sub-pixel form of Upsample)
     note("k_conv_tc3",
-         has_view ? vw.alg_flops : alg_flops >= 0 ? alg_flops : 2.0 * Ho * Wo * Cout_rows * K, 0);
+         has_view ? vw.alg_flops : alg_flops >= 0 ? alg_flops : 2.0 * Ho * Wo * Cout_rows * K, 0,
+         2.0 * Ho * Wo * Cout_rows * K);
     *out = o;
     return EO_OK;
   }
@@ -847,7 +853,8 @@ struct eo_unet {
       EO_CHECK_CUDA(cudaStreamSynchronize(st));   // rmap is a stack-lifetime host buffer
       Act qkv;
       rc = plan_conv_tc(p + "qkv", {fuse ? with_gn(seg1x1(x), g, 0, 0) : seg1x1(xn)}, {{wq, C, 1, 0, C}}, rows, d_rmap,
-                        w(p + "qkv.bias"), nullptr, -1, nullptr, x.H, x.W, &qkv, st, /*want_stats=*/false);
+                        w(p + "qkv.bias"), nullptr, -1, nullptr, x.H, x.W, &qkv, st, /*want_stats=*/false, nullptr,
+                        /*alg_flops=*/2.0 * x.H * x.W * 3.0 * C * C);
       if (rc) return rc;
       if (fuse) free_gn(g);
       // head dimension < 64: padded channel 63 of every head's v becomes 1.0 (zero weight row, bias 1), so the
@@ -870,7 +877,7 @@ struct eo_unet {
         return tc_attn_plan_create(ap, &attn_plans[ai]);
       };
       push(p + "attention", [=](int B, cudaStream_t stx) -> int { return tc_attn_launch(attn_plans[ai], B, stx); }, 1, prepare);
-      note("k_attn_tc", 4.0 * heads * (double)T * T * ch, 0);
+      note("k_attn_tc5", 4.0 * heads * (double)T * T * ch, 0, 4.0 * heads * (double)T * T * 64);
       free_act(qkv);
       rc = plan_conv_tc(p + "proj_out", {seg1x1(a)}, {{wp, C, 1, 0, C}}, C, nullptr, w(p + "proj_out.bias"), nullptr, -1, &x,
                         x.H, x.W, out, st);
@@ -1059,7 +1066,7 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
     push("time_embed", [=](int B, cudaStream_t s) -> int {
       // a precomputed table serves every forward without class labels (label_emb(y) is added BEFORE the
       // projections, :764-766, so those rows depend on (t, y))
-      if (tt_table && !io_y) return launch_gather_rows(tt_table, tt_n, tb_total, io_t, B, tb, s);
+      if (tt_on && tt_table && !io_y) return launch_gather_rows(tt_table, tt_n, tb_total, io_t, B, tb, s);
       int r = launch_sinusoid(io_t, freqs, B, mc / 2, e0, s);
       if (r) return r;
       if ((r = launch_linear(e0, w0, b0, nullptr, nullptr, nullptr, 0, B, mc, ted, l1, s))) return r;
@@ -1245,8 +1252,9 @@ int eo_unet::build_time_tables(int n, cudaStream_t st) {
   EO_REQUIRE(finalized, EO_ERR_STATE, "eo_unet_build_time_tables before eo_unet_finalize");
   EO_REQUIRE(n >= 1 && n <= (1 << 20), EO_ERR_ARG, "eo_unet_build_time_tables: %d timesteps", n);
   EO_REQUIRE(tb_total % 4 == 0, EO_ERR_ARG, "eo_unet_build_time_tables: table width %d", tb_total);
-  if (tt_table && tt_n >= n) return EO_OK;
+  if (tt_table && tt_n >= n) { tt_on = true; return EO_OK; }
   release_time_tables();
+  release_graphs_only();            // graphs captured with the old table's address
   const int mc = cfg.model_channels;
   float *t_e0 = nullptr, *t_l1 = nullptr, *t_emb = nullptr;
   int64_t* t_idx = nullptr;
@@ -1261,7 +1269,7 @@ int eo_unet::build_time_tables(int n, cudaStream_t st) {
     set_error("eo_unet_build_time_tables: %s", cudaGetErrorString(e));
     return EO_ERR_CUDA;
   }
-  tt_n = n;
+  tt_n = n; tt_on = true;
   dev_bytes += (int64_t)n * tb_total * sizeof(float);
   int rc = launch_iota64(t_idx, n, st);
   if (!rc) rc = launch_sinusoid(t_idx, w("time_embed.freqs"), n, mc / 2, t_e0, st);
@@ -1339,7 +1347,7 @@ int eo_unet::run_ops(int B, cudaStream_t st) {
 int eo_unet::forward_graph(const float* x, int Cx, const float* cond, int Cc, const int64_t* t, const int64_t* y,
                            float* out, int B, cudaStream_t st, bool* handled) {
   *handled = false;
-  const long long key = ((((long long)B * 64 + Cx) * 64 + Cc) * 2 + (y ? 1 : 0)) * 2 + (tt_table ? 1 : 0);
+  const long long key = ((((long long)B * 64 + Cx) * 64 + Cc) * 2 + (y ? 1 : 0)) * 2 + (tt_on ? 1 : 0);
   GraphSlot& g = graphs[key];
   if (g.failed || ++g.seen == 1) return EO_OK;
   const size_t hw = (size_t)H * W;
@@ -1509,9 +1517,14 @@ int eo_unet_op_info(const eo_unet* u, int index, const char** name, const char**
   return EO_OK;
 }
 
+double eo_unet_op_executed_flops(const eo_unet* u, int index) {
+  if (!u || !u->finalized || index < 0 || index >= (int)u->ops.size()) return -1.0;
+  return u->ops[index].exec_flops;
+}
+
 int64_t eo_unet_device_bytes(const eo_unet* u) { return u ? u->dev_bytes : 0; }
 // + the two GN memsets; with timestep tables installed the embedding path is one gather instead of four launches
-int eo_unet_launches_per_forward(const eo_unet* u) { return u ? u->n_launches + 2 - (u->tt_table ? 3 : 0) : 0; }
+int eo_unet_launches_per_forward(const eo_unet* u) { return u ? u->n_launches + 2 - (u->tt_on ? 3 : 0) : 0; }
 
 int eo_unet_build_time_tables(eo_unet* u, int n_timesteps, void* stream) {
   EO_REQUIRE(u, EO_ERR_ARG, "eo_unet_build_time_tables: null handle");
@@ -1669,7 +1682,10 @@ int eo_sample_ddpm(eo_unet* u, float* x, const float* noise_tape, const float* g
   const size_t n = (size_t)B * Cx * HW;
   int rc;
   // the loop visits the timestep values T-1 .. 0: their embedding rows are computed once, not once per step
+  // (the table stays cached in the handle; forwards outside this loop use it only if the caller installed it)
+  const bool tt_prev = u->tt_on;
   if (!y && (rc = u->build_time_tables(T, (cudaStream_t)stream))) return rc;
+  struct Restore { eo_unet* u; bool prev; ~Restore() { u->tt_on = prev; } } restore{u, tt_prev};
   if (gt && (rc = eo_ddpm_sum_mix(x, gt, mask, noise_tape, timestep_rows + (size_t)(T - 1) * B, table, x, B, Cx, HW, stream)))
     return rc;
   for (int i = T - 1; i >= 0; --i) {

@@ -139,6 +139,11 @@ EO_API int eo_unet_num_ops(const eo_unet* u);
 EO_API int eo_unet_op_info(const eo_unet* u, int index, const char** name, const char** kernel,
                     double* flops_per_image, double* bytes_per_image);
 
+/* FLOPs op `index` EXECUTES per image (zero-padded qkv / head / stem rows and head-dimension padding count, the
+ * sub-pixel form of Upsample counts 4/9): the figure to hold against ncu's tensor-pipe utilisation, next to the
+ * algorithmic one of eo_unet_op_info.  Negative on a bad index. */
+EO_API double eo_unet_op_executed_flops(const eo_unet* u, int index);
+
 /* bytes of device memory held by the engine (packed weights + workspace) */
 EO_API int64_t eo_unet_device_bytes(const eo_unet* u);
 /* number of kernel launches one eo_unet_forward enqueues (for bench.py's gpu_launches) */
@@ -208,8 +213,8 @@ EO_API int eo_ddpm_step_mix(const float* x_t, const float* eps, const float* noi
  *   table         [T][EO_DDPM_NCOEF], see above
  *   eps_scratch   [B, out_channels, H, W] work buffer for the UNet output
  * Same kernels in the same order as the per-step entry points: bit-identical to driving them from the host.
- * B, Cx, H, W must match the finalized geometry (batch <= max_batch); installs the timestep tables of 0 .. T-1
- * (eo_unet_build_time_tables) when y == NULL.
+ * B, Cx, H, W must match the finalized geometry (batch <= max_batch); uses the timestep tables of 0 .. T-1
+ * (eo_unet_build_time_tables) for its own loop when y == NULL and leaves the handle's table setting as it found it.
  * Threading: an eo_unet handle carries per-forward state (staging buffers, CUDA graphs); calls on ONE handle
  * must be serialised by the caller -- use one handle per host thread / device. */
 EO_API int eo_sample_ddpm(eo_unet* u, float* x, const float* noise_tape, const float* gt, const float* mask,

@@ -136,3 +136,45 @@ def test_oracle_vs_live_reference_tiny():
         ref = m(x, t)
     got = O.unet_forward({k: v.detach() for k, v in m.state_dict().items()}, O.full_cfg(**cfg), x, t)
     assert torch.equal(ref, got)
+
+
+# ---- round-2 fixtures (oracle/make_golden_r2.py) -----------------------------------------------------
+@pytest.mark.parametrize("name", ["heads1_eps", "base64_ms_concat_eps"])
+def test_round2_eps_goldens(name):
+    """num_heads = 1 (head dimensions > 64, the reference scripts' own setting) and the 13 + 15 -> 13 channel stem / head
+    at base width: the oracle reproduces the live reference's eps from the seeds the fixture stores."""
+    g = golden(name)
+    cfg = golden_cfg(g)
+    m = _ref_unet(cfg, int(g["init_seed"]), int(g["dezero_seed"]))
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    assert weight_checksum(sd) == json.loads(str(g["wsum"]))["sha256"]
+    gen = torch.Generator().manual_seed(int(g["x_seed"]))
+    B, cc, size = len(g["t"]), int(g["cond_ch"]), cfg["image_size"]
+    x = torch.randn((B, cfg["in_channels"] - cc, size, size), generator=gen)
+    cond = torch.rand((B, cc, size, size), generator=gen) if cc else None
+    got = O.unet_forward(sd, O.full_cfg(**cfg), x, tt(g["t"]), cond=cond)
+    assert O.rel_l2(got, tt(g["eps"])) < 1e-6
+
+
+def test_round2_cfg_ddim_golden():
+    """Classifier-free guidance (ddim.py:176-181) in the oracle against the live reference's DDIMSampler.sample."""
+    g = golden("tiny_cfg_ddim_S4_T8")
+    cfg = golden_cfg(g)
+    m = _ref_unet(cfg, int(g["init_seed"]), int(g["dezero_seed"]))
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    n, S = int(g["n"]), 4
+    x_T, tape = O.noise_tape((n, 3, 16, 16), S, seed=int(g["tape_seed"]))
+    cond = tt(g["cond"])
+    got, inter = O.ddim_sample(sd, O.full_cfg(**cfg), O.cosine_schedule(8), S, x_T, tape, eta=float(g["eta"]), cond=cond,
+                               log_every_t=1, unconditional_guidance_scale=float(g["scale"]),
+                               unconditional_conditioning=torch.zeros_like(cond))
+    assert O.rel_l2(got, tt(g["x0"])) < 1e-5
+    assert O.rel_l2(inter["pred_x0"][-1], tt(g["pred_x0_last"])) < 1e-5
+
+
+def test_round2_manifest_pins():
+    with open(os.path.join(GOLD, "MANIFEST.json")) as f:
+        cases = json.load(f)["cases"]
+    for name in ("base128_eps_b2", "base256_eps_b2", "base64_ms_concat_eps", "heads1_eps", "base64_ddpm_sum_T1000",
+                 "tiny_cfg_ddim_S4_T8", "tiny_forward_train"):
+        assert cases[name]["oracle_vs_reference"] == "bit-exact", name
