@@ -10,7 +10,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libeo_b200.so")
+# EO_B200_LIB: load another build of the library (a path, e.g. an A/B variant produced by build(variant=...))
+LIB_PATH = os.environ.get("EO_B200_LIB") or os.path.join(HERE, "libeo_b200.so")
 
 EO_OK = 0
 EO_MODE_FP32 = 0

@@ -31,11 +31,15 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    """variant (development, tools/ab_build.sh): a differently compiled copy `libeo_b200_<variant>.so` with its own
+    object directory, EO_NVCC_EXTRA carrying its -D switches; `_lib` loads it when EO_B200_LIB names it."""
     nvcc = _nvcc()
+    variant = variant or os.environ.get("EO_LIB_VARIANT", "")
+    lib = LIB if not variant else os.path.join(HERE, f"libeo_b200_{variant}.so")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "eo_b200.h"))
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + (f"_{variant}" if variant else ""))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
@@ -55,10 +59,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
+    if force or procs or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lcudart"]
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -588,6 +588,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster_relaxed(tmem_empty_leader + ab * 8);
           }
+          if (to_nchw && half * 32 >= ep.out_nchw_C) continue;      // padded channels of the head: nothing to write
           if (cache_bias) {
             if (valid) {
               const float* wr = wb + ((c - set) >> 1) * 64 + half * 32;
@@ -626,11 +627,15 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           if (to_nchw) {
             // network output: fp32 planes, 8 consecutive pixels of a row per 8 lanes (32-byte segments)
             if (valid) {
-              float* op = ep.out_nchw + (((long long)n_img * ep.out_nchw_C) * g.H + (t.h0 + pix_h)) * g.W + t.w0 + pix_w;
               const long long plane = (long long)g.H * g.W;
+              float* op = ep.out_nchw + (((long long)n_img * ep.out_nchw_C + half * 32) * g.H + (t.h0 + pix_h)) * g.W + t.w0 + pix_w;
+              const int nj = ep.out_nchw_C - half * 32;          // warp-uniform: the loop leaves after the real channels
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (half * 32 + j < ep.out_nchw_C) op[(half * 32 + j) * plane] = f[j];
+              for (int j = 0; j < 32; ++j) {
+                if (j >= nj) break;
+                *op = f[j];
+                op += plane;
+              }
             }
           } else {
 #pragma unroll
