@@ -37,6 +37,7 @@
 #include "kernels.h"
 #include "tc_common.cuh"
 #include "tc_conv_plan.h"
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -54,6 +55,7 @@ constexpr int A_STAGE = 23552;                             // 23 KB: PATCH_BYTES
 constexpr int SA_MAX = 4;                                  // operand-A stages: SAR filled by TMA + SAG by the transform warps
 constexpr int STG_BYTES = BM * 128;                        // one 128-row x 64-channel bf16 tile
 constexpr int MAX_ENT = 176;
+constexpr int MAX_XENT = 32;                               // GroupNorm-folded patch loads per tile (<= 2048 channels)
 constexpr int MAX_SB = 12;
 constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;
 constexpr int SMEM_LIMIT = 232448;                         // 227 KB per CTA
@@ -67,7 +69,8 @@ constexpr int XF_PIX = (PATCH_W * PATCH_H + 4 * XF_WARPS - 1) / (4 * XF_WARPS); 
 struct Smem {
   static constexpr int STG_OFF = 0;                                    // 2 staging tiles
   static constexpr int TAB_OFF = STG_OFF + 2 * STG_BYTES;
-  static constexpr int STAT_OFF = TAB_OFF + MAX_ENT * (int)sizeof(KEnt3);   // [4 warps][256][2] floats
+  static constexpr int XTAB_OFF = TAB_OFF + MAX_ENT * (int)sizeof(KEnt3);   // the GroupNorm-folded loads, resolved
+  static constexpr int STAT_OFF = XTAB_OFF + MAX_XENT * (int)sizeof(XEnt3);  // [4 warps][256][2] floats
   static constexpr int WB_OFF = STAT_OFF + 4 * 256 * 2 * 4;            // [8 epilogue warps][2 chunks][64] floats: bias + timestep row
   static constexpr int BAR_OFF = WB_OFF + 8 * 128 * 4;
   // r_full r_empty g_ready g_empty [SA_MAX each] b_full[MAX_SB] b_empty[MAX_SB] tmem_full[2] tmem_empty[2]
@@ -114,7 +117,7 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ void trace_put(const Epi3& ep, int slot, long long v) {
   if (!ep.trace || (int)blockIdx.x >= ep.trace_n) return;
   if (slot < 8) ep.trace[(long long)blockIdx.x * 8 + slot] = v;
-  else if (ep.trace_ext) ep.trace[((long long)ep.trace_n + blockIdx.x) * 8 + slot - 8] = v;
+  else if (ep.trace_ext) ep.trace[((long long)ep.trace_n * (slot >> 3) + blockIdx.x) * 8 + (slot & 7)] = v;   // trace_ext: 4 * n * 8 counters
 }
 #define TRACE_T0() const long long _t0 = TRACE ? clock64() : 0
 #define TRACE_ACC(var) do { if (TRACE) (var) += clock64() - _t0; } while (0)
@@ -130,13 +133,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
            const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
            const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
-           const KEnt3* __restrict__ ents, int nent, Geom3 g, int B, int BN, int SB, int TPB, int SAR, int SAG, int n_work,
-           int n_ntiles, Epi3 ep) {
+           const KEnt3* __restrict__ ents, int nent, const XEnt3* __restrict__ xents, int n_xent, Geom3 g, int B, int BN,
+           int SB, int TPB, int SAR, int SAG, int n_work, int n_ntiles, Epi3 ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_a = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);   // operand-A stages
   uint8_t* smem = smem_a + (SAR + SAG) * A_STAGE;                                    // everything else
   uint8_t* smem_g = smem_a + SAR * A_STAGE;                                          // the transform warps' stages
   KEnt3* tab = reinterpret_cast<KEnt3*>(smem + Smem::TAB_OFF);
+  XEnt3* xtab = reinterpret_cast<XEnt3*>(smem + Smem::XTAB_OFF);
   float* sstat = reinterpret_cast<float*>(smem + Smem::STAT_OFF);
   // Operand A has two rings, one per filler, so that nobody has to track a stage it does not fill: stages
   // loaded by TMA as is (both CTAs' bytes complete on the leader's r_full), and stages the transform warps
@@ -183,6 +187,8 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   }
   if (warp == 1) { tc::tmem_alloc2(tmem_ptr, TMEM_COLS); tc::tmem_relinquish2(); }
   for (int i = threadIdx.x; i < nent; i += blockDim.x) tab[i] = ents[i];
+  for (int i = threadIdx.x; i < n_xent * (int)(sizeof(XEnt3) / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(xtab)[i] = reinterpret_cast<const uint4*>(xents)[i];
   tc::tc_fence_before();
   tc::cluster_sync_all();                    // peer barriers are initialised past here
   tc::tc_fence_after();
@@ -204,10 +210,12 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const uint32_t r_full_l = tc::mapa_u32(tc::smem_u32(&r_full[0]), 0);   // the leader's barriers
     const uint32_t b_full_l = tc::mapa_u32(tc::smem_u32(&b_full[0]), 0);
     const int b_row = (int)rank * (BN / 2);
+    KEnt3 en_next = tab[0];           // the table is read one entry ahead: an ld.shared takes ~200 clk here
     for (int w = cid; w < n_work; w += ncl) {
       const Tile t = decode_tile(w, n_ntiles, rank, g, BN);
       for (int e = 0; e < nent; ++e) {
-        const KEnt3 en = tab[e];
+        const KEnt3 en = en_next;
+        en_next = tab[e + 1 == nent ? 0 : e + 1];
         if (!en.gn) { TRACE_T0(); tc::mbar_wait(&r_empty[ra.i], ra.ph ^ 1); TRACE_ACC(tr_wait); }
         const CUtensorMap* ma = en.seg == 0 ? &mapA0 : (en.seg == 1 ? &mapA1 : &mapA2);
         if (!en.gn && tc::elect_one()) {
@@ -257,6 +265,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       Ring ra, rg, rb;
       uint32_t it = 0;
       long long tr_ops = 0, tr_acc = 0, tr_a = 0;
+      int pg_next = tab[0].patch | (tab[0].gn << 8);      // (patch, gn) of the next entry, read one entry ahead
       for (int w = cid; w < n_work; w += ncl, ++it) {
         const uint32_t ab = it & 1;
         { TRACE_T0(); tc::mbar_wait_cluster(&tmem_empty[ab], ((it >> 1) & 1) ^ 1); TRACE_ACC(tr_acc); }   // both CTAs' epilogues drained this buffer
@@ -264,8 +273,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         const uint32_t d_tmem = tmem_base + ab * ACC_STRIDE;
         uint32_t acc = 0;
         for (int e = 0; e < nent; ++e) {
-          const int patch = tab[e].patch;
-          const bool gn = tab[e].gn != 0;
+          const int patch = pg_next & 0xff;
+          const bool gn = (pg_next >> 8) != 0;
+          { const int e1 = e + 1 == nent ? 0 : e + 1; pg_next = tab[e1].patch | (tab[e1].gn << 8); }
           {
             TRACE_T0();
             if (gn) tc::mbar_wait_cluster(&g_ready[rg.i], rg.ph);
@@ -367,19 +377,27 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       ptab[i] = (uint32_t)(q * 128 + ((ch8 ^ (q & 7)) << 4)) | (edge << 16);
       plin[i] = (uint32_t)(ph * g.W + pw);
     }
-    // cursor over the GroupNorm-folded operand loads of this CTA, in the order the MMA warp consumes them
-    struct Cur { int w, e; Ring ring; Tile t; bool valid; };
-    auto seek = [&](Cur& c, bool first) {      // advance to the next such load (or the first one)
-      for (;;) {
-        if (!first) {
-          if (tab[c.e].gn) c.ring.next((uint32_t)SAG);
-          if (++c.e == nent) { c.e = 0; c.w += ncl; }
-        }
-        first = false;
+    // Cursor over the GroupNorm-folded operand loads of this CTA, in the order the MMA warp consumes them: load j of
+    // the compact list `xtab` (one XEnt3 per such load, resolved pointers included) of tile w.  With the tensor core
+    // streaming operands out of the same shared memory an ld.shared takes ~200 clk, and the walk used to make five
+    // DEPENDENT reads of the operand table per patch (the gn flags while seeking, the entry for its affine rows, again
+    // for the patch loads, again for the SiLU flag: 1280 clk of set-up per patch in the per-CTA trace, on the critical
+    // path of every Cout = 128 layer).  Now every entry is read ONCE, a whole patch before it is needed.
+    struct Cur { int w, j; Ring ring; Tile t; bool valid; };
+    auto advance = [&](Cur& c) {
+      c.ring.next((uint32_t)SAG);
+      if (++c.j == n_xent) {
+        c.j = 0; c.w += ncl;
         if (c.w >= n_work) { c.valid = false; return; }
-        if (c.e == 0) c.t = decode_tile(c.w, n_ntiles, rank, g, BN);
-        if (tab[c.e].gn) { c.valid = true; return; }
+        c.t = decode_tile(c.w, n_ntiles, rank, g, BN);
       }
+    };
+    auto read_xent = [&](int j) -> XEnt3 {
+      XEnt3 x;
+      const uint4* q = reinterpret_cast<const uint4*>(xtab + j);
+      uint4* d = reinterpret_cast<uint4*>(&x);
+      d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
+      return x;
     };
     // two patches of 6 x 16 bytes per thread in registers: the loads of patch i+1 are issued BEFORE patch i is
     // transformed (a first version issued them after the hand-over, because fence.proxy.async waits for every
@@ -391,41 +409,33 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     auto edges_of = [&](const Tile& t) -> uint32_t {   // image borders the tile touches (+ "beyond the patch")
       return ((t.h0 == 0 ? 1u : 0u) | (t.h0 + 16 == g.H ? 2u : 0u) | (t.w0 == 0 ? 4u : 0u) | (t.w0 + 8 == g.W ? 8u : 0u) | 16u) << 16;
     };
-    auto src_of = [&](const Cur& c, const KEnt3& en, uint32_t& Cs) -> const uint8_t* {
-      // (constant-index selects: a dynamically indexed kernel parameter array is copied to local memory)
-      const void* sp = en.seg == 0 ? ep.gn_src[0] : (en.seg == 1 ? ep.gn_src[1] : ep.gn_src[2]);
-      Cs = (uint32_t)(en.seg == 0 ? ep.gn_C[0] : (en.seg == 1 ? ep.gn_C[1] : ep.gn_C[2]));
-      const long long pix0 = ((long long)c.t.n0 * g.H + (c.t.h0 - 1)) * g.W + (c.t.w0 - 1);
-      return reinterpret_cast<const uint8_t*>(sp) + (pix0 * (long long)Cs + en.c0 + ch8 * 8) * 2;
-    };
-    auto load_affine = [&](const Cur& c, const KEnt3& en) {
+    auto load_affine = [&](const Cur& c, const XEnt3& xe) {
       if (c.t.n0 >= B) return;
-      const float* gsc = en.seg == 0 ? ep.gn_scale[0] : (en.seg == 1 ? ep.gn_scale[1] : ep.gn_scale[2]);
-      const float* gsh = en.seg == 0 ? ep.gn_shift[0] : (en.seg == 1 ? ep.gn_shift[1] : ep.gn_shift[2]);
-      const int gld = en.seg == 0 ? ep.gn_ld[0] : (en.seg == 1 ? ep.gn_ld[1] : ep.gn_ld[2]);
-      const long long o = (long long)c.t.n0 * gld + en.gnc + ch8 * 8;
-      na0 = __ldg(reinterpret_cast<const float4*>(gsc + o));
-      na1 = __ldg(reinterpret_cast<const float4*>(gsc + o + 4));
-      nb0 = __ldg(reinterpret_cast<const float4*>(gsh + o));
-      nb1 = __ldg(reinterpret_cast<const float4*>(gsh + o + 4));
+      const long long o = (long long)c.t.n0 * xe.gld + ch8 * 8;
+      const float* gsc = reinterpret_cast<const float*>(xe.gsc) + o;
+      const float* gsh = reinterpret_cast<const float*>(xe.gsh) + o;
+      na0 = __ldg(reinterpret_cast<const float4*>(gsc));
+      na1 = __ldg(reinterpret_cast<const float4*>(gsc + 4));
+      nb0 = __ldg(reinterpret_cast<const float4*>(gsh));
+      nb1 = __ldg(reinterpret_cast<const float4*>(gsh + 4));
     };
-    auto load_patch = [&](const Cur& c, uint4 (&buf)[XF_PIX]) {
-      const KEnt3 en = tab[c.e];
-      uint32_t Cs;
-      const uint8_t* src = src_of(c, en, Cs);
+    auto load_patch = [&](const Cur& c, const XEnt3& xe, uint4 (&buf)[XF_PIX]) {
+      const long long pix0 = ((long long)c.t.n0 * g.H + (c.t.h0 - 1)) * g.W + (c.t.w0 - 1);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(xe.src) + pix0 * (long long)xe.cs2 + ch8 * 16;
       const uint32_t te = c.t.n0 < B ? edges_of(c.t) : 0xffffffffu;
-      const uint32_t cs2 = Cs * 2u;          // pixel pitch in bytes; plin * cs2 < 2^32 (one image plane of <= 2048 channels)
 #pragma unroll
-      for (int i = 0; i < XF_PIX; ++i)
-        if (!(ptab[i] & te)) buf[i] = __ldg(reinterpret_cast<const uint4*>(src + (unsigned long long)plin[i] * cs2));
+      for (int i = 0; i < XF_PIX; ++i)      // plin * cs2 < 2^32 (one image plane of <= 2048 channels)
+        if (!(ptab[i] & te)) buf[i] = __ldg(reinterpret_cast<const uint4*>(src + (unsigned long long)plin[i] * xe.cs2));
     };
     long long tr_xb = 0, tr_xw = 0;
-    // transform the patch in `buf` (cursor `cur`) while the loads of the next one (`nxt`) are in flight in `bufn`
+    // transform the patch in `buf` (cursor `cur`, entry `xc`) while the loads of the next one (`nxt`, entry `xn`) are in
+    // flight in `bufn`; `xn2` = the entry after that, read now and first used a whole patch from now
     long long tr_xp = 0;
+    long long tr_f[4 + XF_PIX] = {};        // TRACE: advance + entry read, patch-load issue, each pixel chunk, fence, arrive
+    XEnt3 xc, xn;
     auto step = [&](Cur& cur, uint4 (&buf)[XF_PIX], uint4 (&bufn)[XF_PIX]) {
       const long long t_p0 = TRACE ? clock64() : 0;
-      const KEnt3 en = tab[cur.e];
-      const bool silu = en.gn == 2;
+      const bool silu = xc.silu != 0;
       const uint32_t te = cur.t.n0 < B ? edges_of(cur.t) : 0xffffffffu;
       // scale / shift of this thread's 8 channels.  With SiLU they are halved: silu(y) = h + h tanh(h),
       // h = y/2 (common.cuh silu_f), and 0.5 * fma(x, s, b) == fma(x, 0.5 s, 0.5 b) exactly.
@@ -436,14 +446,19 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       const uint64_t b01 = tc::pack2(nb0.x * hf, nb0.y * hf), b23 = tc::pack2(nb0.z * hf, nb0.w * hf);
       const uint64_t b45 = tc::pack2(nb1.x * hf, nb1.y * hf), b67 = tc::pack2(nb1.z * hf, nb1.w * hf);
       Cur nxt = cur;
-      seek(nxt, false);
+      advance(nxt);
+      const XEnt3 xn2 = read_xent(nxt.j + 1 == n_xent ? 0 : nxt.j + 1);
+      if (TRACE) { const long long c = clock64(); tr_f[0] += c - t_p0; }
       if (nxt.valid) {
-        load_affine(nxt, tab[nxt.e]);
-        load_patch(nxt, bufn);
+        load_affine(nxt, xn);
+        if (TRACE) tr_f[1] -= clock64();
+        load_patch(nxt, xn, bufn);
+        if (TRACE) tr_f[1] += clock64();
       }
       if (TRACE) tr_xp += clock64() - t_p0;
       { TRACE_T0(); tc::mbar_wait(&g_empty[cur.ring.i], cur.ring.ph ^ 1); TRACE_ACC(tr_xw); }   // the MMAs that read this stage have retired
       const long long t_b0 = TRACE ? clock64() : 0;
+      long long t_it = t_b0;
       uint8_t* st = smem_g + cur.ring.i * A_STAGE;
       // one bf16 pair: affine (+ SiLU) in fp32, back to bf16
       auto xf2 = [&](uint32_t in, uint64_t sc, uint64_t sh, bool act) -> uint32_t {
@@ -474,18 +489,24 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           v.w = xf2(v.w, a67, b67, silu);
         }
         *reinterpret_cast<uint4*>(st + (ptab[i] & 0xffffu)) = v;    // zeros outside the image
+        if (TRACE) { const long long c = clock64(); tr_f[2 + i] += c - (i ? t_it : t_b0); t_it = c; }
       }
       tc::fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's operand reads
+      if (TRACE) { const long long c = clock64(); tr_f[2 + XF_PIX] += c - t_it; t_it = c; }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_remote(g_ready_l + cur.ring.i * 8);
+      if (TRACE) { tr_f[3 + XF_PIX] += clock64() - t_it; }
       if (TRACE) tr_xb += clock64() - t_b0;
       cur = nxt;
+      xc = xn; xn = xn2;
     };
-    Cur cur{cid, 0, Ring(), Tile(), false};
-    seek(cur, true);
+    Cur cur{cid, 0, Ring(), Tile(), n_xent > 0 && cid < n_work};
     if (cur.valid) {
-      load_affine(cur, tab[cur.e]);
-      load_patch(cur, bufa);
+      cur.t = decode_tile(cur.w, n_ntiles, rank, g, BN);
+      xc = read_xent(0);
+      xn = read_xent(n_xent > 1 ? 1 : 0);
+      load_affine(cur, xc);
+      load_patch(cur, xc, bufa);
     }
     long long tr_xl = 0;
     while (cur.valid) {
@@ -496,8 +517,11 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       if (TRACE) { asm volatile("" :: "r"(bufa[0].x), "r"(bufa[XF_PIX - 1].w) : "memory"); }
       TRACE_ACC(tr_xl);
     }
-    if (TRACE && xt == 0) { trace_put(ep, 7, tr_xb); trace_put(ep, 9, tr_xw); trace_put(ep, 10, tr_xl); trace_put(ep, 11, tr_xp); }
-#undef EO_LOAD_AFFINE
+    if (TRACE && xt == 0) {
+      trace_put(ep, 7, tr_xb); trace_put(ep, 9, tr_xw); trace_put(ep, 10, tr_xl); trace_put(ep, 11, tr_xp);
+#pragma unroll
+      for (int i = 0; i < 4 + XF_PIX; ++i) trace_put(ep, 16 + i, tr_f[i]);
+    }
   } else if (warp >= EPI_WARP0) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ------------------------------------------------------------------ epilogue
@@ -840,8 +864,26 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
       if (rc != EO_OK) return rc;
     }
   }
-  cudaError_t e = cudaMalloc(&pl->d_kblks, tab.size() * sizeof(KEnt3));
-  if (e == cudaSuccess) e = cudaMemcpy(pl->d_kblks, tab.data(), tab.size() * sizeof(KEnt3), cudaMemcpyHostToDevice);
+  // the GroupNorm-folded loads of one tile, in K order, with everything the transform warps need resolved
+  std::vector<XEnt3> xt;
+  for (const KEnt3& e : tab) {
+    if (!e.gn) continue;
+    const TcConvSeg& sg = p.seg[e.seg];
+    XEnt3 x{};
+    x.src = reinterpret_cast<unsigned long long>(sg.ptr) + (unsigned long long)e.c0 * 2;
+    x.gsc = reinterpret_cast<unsigned long long>(sg.gn_scale + e.gnc);
+    x.gsh = reinterpret_cast<unsigned long long>(sg.gn_shift + e.gnc);
+    x.cs2 = (uint32_t)sg.C * 2u; x.gld = (uint32_t)sg.gn_ld; x.silu = e.gn == 2 ? 1u : 0u;
+    xt.push_back(x);
+  }
+  EO_REQUIRE((int)xt.size() <= MAX_XENT, EO_ERR_ARG, "tc_conv3: %d GroupNorm-folded loads per tile (max %d)", (int)xt.size(), MAX_XENT);
+  pl->n_xent = (int)xt.size();
+  const size_t tab_bytes = tab.size() * sizeof(KEnt3), xt_off = (tab_bytes + 15) & ~(size_t)15;
+  cudaError_t e = cudaMalloc(&pl->d_kblks, xt_off + std::max<size_t>(xt.size(), 1) * sizeof(XEnt3));
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_kblks, tab.data(), tab_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !xt.empty())
+    e = cudaMemcpy(reinterpret_cast<uint8_t*>(pl->d_kblks) + xt_off, xt.data(), xt.size() * sizeof(XEnt3), cudaMemcpyHostToDevice);
+  pl->xent_off = xt_off;
   EO_REQUIRE(e == cudaSuccess, EO_ERR_CUDA, "tc_conv3: operand table upload failed: %s", cudaGetErrorString(e));
   return EO_OK;
 }
@@ -919,7 +961,9 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st, float* out_nch
   auto kern = k_conv_tc3<false>;
 #endif
   EO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA[0], pl->mapA[1], pl->mapA[2], pl->mapB, pl->mapOut,
-                                   pl->mapRes, (const KEnt3*)pl->d_kblks, pl->nkb, g, B, BN, SB, TPB, SAR, SAG, n_work, n_ntiles, ep));
+                                   pl->mapRes, (const KEnt3*)pl->d_kblks, pl->nkb,
+                                   (const XEnt3*)(reinterpret_cast<const uint8_t*>(pl->d_kblks) + pl->xent_off), pl->n_xent, g, B,
+                                   BN, SB, TPB, SAR, SAG, n_work, n_ntiles, ep));
   return EO_OK;
 }
 

@@ -12,6 +12,11 @@ namespace eo {
 //   gnc = first channel of this load in the scale/shift rows;
 //   sc = 1, or 2 for a stride-2 source (the tile origin is doubled: the segment's tensor map walks every second pixel)
 struct KEnt3 { int seg, c0, dhw, dn, kofs, patch, gn, gnc, sc; };   // dhw: dh in the low 16 bits, dw in the high
+// One GroupNorm-folded patch load with its pointers resolved (what the transform warps need, 48 bytes = three 16-byte
+// shared-memory reads made a whole patch ahead): src = the segment's activation at channel c0 (bytes), gsc / gsh = its
+// scale / shift rows at that channel (row of image n: + n * gld floats), cs2 = pixel pitch in bytes
+struct XEnt3 { unsigned long long src, gsc, gsh; unsigned cs2, gld, silu, pad0; unsigned long long pad1; };
+static_assert(sizeof(XEnt3) == 48, "XEnt3 is read as three uint4");
 // division by a launch-time constant as multiply-high + shift (exact for dividends below 2^31): the generic
 // integer division sequence is ~35 dependent instructions, and every warp role decodes a tile index per tile
 struct FastDiv {
@@ -56,8 +61,10 @@ struct TcConvPlan {
   CUtensorMap mapA[3];
   CUtensorMap mapB;
   CUtensorMap mapOut, mapRes;   // v3: TMA store of the output, TMA load of the residual
-  void* d_kblks = nullptr;
+  void* d_kblks = nullptr;      // KEnt3[nkb], then (at xent_off bytes) XEnt3[n_xent]
   int nkb = 0;
+  int n_xent = 0;
+  size_t xent_off = 0;
   Geom3 g3{};
   int bn_tile = 128;
   TcConvParams p;

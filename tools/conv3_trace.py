@@ -26,13 +26,13 @@ def run(B, H, W, Cin, Cout, k, res):
                                                 B, H, W, Cin, Cout, k, _lib.stream_ptr()), "conv")
     call()
     torch.cuda.synchronize()
-    tr = torch.zeros((296, 8), dtype=torch.int64, device=dev)
+    tr = torch.zeros((4 * 148, 8), dtype=torch.int64, device=dev)
     L.eo_debug_conv_trace(_lib.ptr(tr), 148)
     call()
     torch.cuda.synchronize()
     L.eo_debug_conv_trace(None, 0)
     full = tr.cpu().numpy()
-    t, ext = full[:148], full[148:]
+    t, ext, ext2 = full[:148], full[148:296], full[296:].reshape(2, 148, 8)
     lead = t[t[:, 6] > 0]                       # leader CTAs carry the MMA warp's tile count
     tiles = np.median(lead[:, 6])
     f = lambda a, c: np.median(a[:, c]) / tiles
@@ -49,6 +49,14 @@ def run(B, H, W, Cin, Cout, k, res):
         ea = ext[t[:, 0] > 0]
         print(f"   epilogue warp 0: tcgen05.ld + wait {np.median(ea[:, 4]) / tiles:.0f}, bias/residual/pack/stage {np.median(ea[:, 5]) / tiles:.0f}, "
               f"statistics read-back {np.median(ea[:, 6]) / tiles:.0f}, combine + barriers {np.median(ea[:, 7]) / tiles:.0f}")
+
+
+    if ext2.any():
+        live = t[:, 0] > 0
+        f2 = np.concatenate([ext2[0][live], ext2[1][live]], axis=1)
+        v = [np.median(f2[:, i]) / tiles for i in range(10)]
+        print("   transform warp 0 per tile: advance + entry read %.0f, patch-load issue %.0f, pixel chunks %s, fence %.0f, arrive %.0f"
+              % (v[0], v[1], " ".join("%.0f" % x for x in v[2:8]), v[8], v[9]))
 
 
 if __name__ == "__main__":
