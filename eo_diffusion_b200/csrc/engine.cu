@@ -1194,21 +1194,11 @@ int eo_unet::finalize(int mode_, int Bmax_, int H_, int W_, cudaStream_t st) {
     if ((rc = dmalloc(&d_rmap, (size_t)64))) return rc;
     EO_CHECK_CUDA(cudaMemcpyAsync(d_rmap, rmap.data(), 64 * sizeof(int), cudaMemcpyHostToDevice, st));
     EO_CHECK_CUDA(cudaStreamSynchronize(st));   // rmap is a stack-lifetime host buffer
-#ifdef EO_HEAD_NHWC      // experiment: the padded bf16 NHWC head + layout pass
-    Act o64;
-    if ((rc = plan_conv_tc("out", {with_gn(seg3x3(h), g, 0, 1)}, {{w("out.2.weight"), C, 3, 0, C}}, 64, d_rmap, w("out.2.bias"),
-                           nullptr, -1, nullptr, H, W, &o64, st, false, nullptr, 2.0 * H * W * cout * 9 * C)))
-      return rc;
-    free_gn(g);
-    push("out.nchw", [=](int B, cudaStream_t s) -> int { return launch_head_to_nchw(ptr(o64.off), 64, io_out, B, H * W, cout, s); });
-    note("k_head_to_nchw", 0, (double)H * W * (32 + cout * 4));
-#else
     Act none;
     if ((rc = plan_conv_tc("out", {with_gn(seg3x3(h), g, 0, 1)}, {{w("out.2.weight"), C, 3, 0, C}}, 64, d_rmap, w("out.2.bias"),
                            nullptr, -1, nullptr, H, W, &none, st, false, nullptr, 2.0 * H * W * cout * 9 * C, cout)))
       return rc;
     free_gn(g);
-#endif
   } else {
     GnOut g = plan_gn("out.0", h, nullptr, w("out.0.weight"), w("out.0.bias"));
     float* Wp = nullptr; int K = 0;

@@ -114,9 +114,6 @@ int launch_attention_wide(const void* qkv, void* out, int dt, int B, int T, int 
 // ---------------------------------------------------------------------------------------
 // dst[b,2h+i,2w+j,c] = src[b,h,w,c]
 int launch_upsample2x(const void* src, void* dst, int B, int H, int W, int C, cudaStream_t st);
-// dst[(hp*2+wp)][b][h2][w2][c] = src[b][2*h2+hp][2*w2+wp][c]; planes are Bstride images apart
-int launch_space_to_depth(const void* src, void* dst, int B, int Bstride, int H, int W, int C,
-                          cudaStream_t st);
 // dst[b, ho, wo, coff + c] = resample(act(src * scale[b, gc + c] + shift[b, gc + c])): mode 0 same grid, 1 nearest x2,
 // 2 average of 2x2; scale/shift may be null; src/dst NHWC of dtype dt (up/down ResBlocks, unet_openai.py:366-371)
 int launch_resample(const void* src, int Cs, void* dst, int Cd, int coff, int dt, int B, int Hi, int Wi, int mode,
@@ -131,8 +128,6 @@ int launch_stem_weight(const float* w, int Cout, int C, float* w2, cudaStream_t 
 // matching [Cout][64][3][3] fp32 weights; the stem is then a plain 3x3 tensor-core conv
 int launch_stem_nhwc(const float* x, int Cx, const float* cond, int Cc, void* dst, int B, int H, int W, cudaStream_t st);
 int launch_stem_weight3(const float* w, int Cout, int C, float* w2, cudaStream_t st);
-// tensor-core head: the first C of `ld` channels of a bf16 NHWC tensor -> NCHW fp32
-int launch_head_to_nchw(const void* src_bf16, int ld, float* dst, int B, int HW, int C, cudaStream_t st);
 // generic NHWC (dt) -> NCHW fp32 copy, for eo_unet_read_activation
 int launch_nhwc_to_nchw_f32(const void* src, int dt, float* dst, int B, int HW, int C,
                             cudaStream_t st);

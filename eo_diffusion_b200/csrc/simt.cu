@@ -1032,22 +1032,6 @@ k_upsample2x(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int 
     dst[i] = __ldg(src + ((b * H + (oh >> 1)) * W + (ow >> 1)) * C8 + c);
   }
 }
-// stride-2 conv operand regrouping: 4 parity planes so every tap is a unit-stride window
-__global__ void __launch_bounds__(256)
-k_space_to_depth(const uint4* __restrict__ src, uint4* __restrict__ dst, int Bstride, int H, int W,
-                 int C8, long long total) {
-  const int H2 = H / 2, W2 = W / 2;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C8);
-    long long r = i / C8;
-    int w = (int)(r % W); r /= W;
-    int h = (int)(r % H);
-    long long b = r / H;
-    int plane = (h & 1) * 2 + (w & 1);
-    dst[((((long long)plane * Bstride + b) * H2 + (h >> 1)) * W2 + (w >> 1)) * C8 + c] = __ldg(src + i);
-  }
-}
 __global__ void __launch_bounds__(256)
 k_nhwc_to_nchw(const void* __restrict__ src, int dt, float* __restrict__ dst, int HW, int C,
                long long total) {
@@ -1078,16 +1062,6 @@ int launch_upsample2x(const void* src, void* dst, int B, int H, int W, int C, cu
   return EO_OK;
 }
 
-int launch_space_to_depth(const void* src, void* dst, int B, int Bstride, int H, int W, int C,
-                          cudaStream_t st) {
-  EO_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, EO_ERR_ARG, "space_to_depth: shape");
-  long long total = (long long)B * H * W * (C / 8);
-  k_space_to_depth<<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
-                                                   reinterpret_cast<uint4*>(dst), Bstride, H, W, C / 8,
-                                                   total);
-  EO_CHECK_LAUNCH();
-  return EO_OK;
-}
 
 int launch_nhwc_to_nchw_f32(const void* src, int dt, float* dst, int B, int HW, int C,
                             cudaStream_t st) {
@@ -1296,22 +1270,6 @@ __global__ void k_stem_weight(const float* __restrict__ w, int Cout, int C, floa
   if (k < 9 * C) { const int tap = k / C, c = k - tap * C; v = w[((long long)n * C + c) * 9 + tap]; }
   w2[i] = v;
 }
-// dst[b, c, p] (NCHW fp32, c < C) = src[b, p, c] (NHWC bf16 with `ld` channels per pixel)
-__global__ void __launch_bounds__(256)
-k_head_to_nchw(const __nv_bfloat16* __restrict__ src, int ld, float* __restrict__ dst, int HW, int C, long long npix) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / HW;
-    const int p = (int)(i - b * HW);
-    const __nv_bfloat16* s = src + i * ld;
-    for (int c0 = 0; c0 < C; c0 += 8) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(s + c0));
-      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&q);
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (c0 + j < C) dst[(b * C + c0 + j) * HW + p] = __bfloat162float(e[j]);
-    }
-  }
-}
 }  // namespace
 
 int launch_stem_im2col(const float* x, int Cx, const float* cond, int Cc, void* dst, int B, int H, int W, cudaStream_t st) {
@@ -1340,13 +1298,6 @@ int launch_stem_weight3(const float* w, int Cout, int C, float* w2, cudaStream_t
 }
 int launch_stem_weight(const float* w, int Cout, int C, float* w2, cudaStream_t st) {
   k_stem_weight<<<ceil_div(Cout * 64, 256), 256, 0, st>>>(w, Cout, C, w2);
-  EO_CHECK_LAUNCH();
-  return EO_OK;
-}
-int launch_head_to_nchw(const void* src_bf16, int ld, float* dst, int B, int HW, int C, cudaStream_t st) {
-  EO_REQUIRE(ld % 8 == 0, EO_ERR_ARG, "head_to_nchw: ld %% 8");
-  const long long npix = (long long)B * HW;
-  k_head_to_nchw<<<ew_grid(npix), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src_bf16), ld, dst, HW, C, npix);
   EO_CHECK_LAUNCH();
   return EO_OK;
 }

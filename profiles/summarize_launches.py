@@ -24,8 +24,10 @@ for r in csv.DictReader(io.StringIO("".join(lines))):
     e = launches.setdefault(r["ID"], {"name": r["Kernel Name"]})
     e[r["Metric Name"]] = float(r["Metric Value"])
 rows = [e for e in launches.values() if "k_pack" not in e["name"]]
-# one sampler step = from one k_sinusoid (first kernel of the UNet forward) to the next
-starts = [i for i, r in enumerate(rows) if "k_sinusoid" in r["name"]]
+# one sampler step = from the first kernel of one UNet forward to the next: k_gather_rows when the sampler hoisted the
+# timestep tables (round 2), k_sinusoid otherwise
+marker = "k_gather_rows" if any("k_gather_rows" in r["name"] for r in rows) else "k_sinusoid"
+starts = [i for i, r in enumerate(rows) if marker in r["name"]]
 if len(starts) >= 2:
     which = min(per_step, len(starts) - 2)
     rows = rows[starts[which]:starts[which + 1]]
