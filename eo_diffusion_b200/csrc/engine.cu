@@ -1533,7 +1533,10 @@ int eo_unet_build_time_tables(eo_unet* u, int n_timesteps, void* stream) {
 
 int eo_unet_clear_time_tables(eo_unet* u) {
   EO_REQUIRE(u, EO_ERR_ARG, "eo_unet_clear_time_tables: null handle");
-  u->release_time_tables();
+  // Only the switch: the rows depend on the timestep value alone, so the table stays valid (and its graphs with it)
+  // for the next sampling loop.  Freeing it here cost a device-wide cudaFree per sampling() call -- measured at up to
+  // 800 ms on a B200 with graphs alive (tools/prof_sampling.py) -- and a graph re-capture per call.
+  u->tt_on = false;
   return EO_OK;
 }
 

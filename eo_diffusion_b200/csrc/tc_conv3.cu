@@ -787,8 +787,23 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
   g.tiles_w = p.W / g.bw; g.tiles_h = p.H / g.bh;
   g.d_tw.set((unsigned)g.tiles_w); g.d_th.set((unsigned)g.tiles_h);
   pl->g3 = g;
+  // Channel-tile width: the widest that divides Cout (fewest re-reads / re-transforms of the activation operand) unless
+  // the problem is so small that it leaves SMs idle (the reference's 64 x 64 batch-1 case, the deep levels of
+  // 128 x 128 batch 16): then the width that minimises waves x cost per 16-deep K step.  Costs are the MEASURED clk per
+  // K step of full launches (per-CTA traces): the tensor pipe's BN / 2 for wide tiles, the
+  // shared-memory port for narrow ones
   int BN = 64;
-  for (int cand : {256, 192, 128, 64}) if (p.Cout % cand == 0) { BN = cand; break; }
+  {
+    const long long mpairs = ((long long)g.tiles_w * g.tiles_h * ceil_div(p.B, g.bn) + 1) / 2;
+    const long long ncl = std::max(1, num_sms() / 2);
+    long long best = -1;
+    for (int cand : {256, 192, 128, 64}) {
+      if (p.Cout % cand != 0) continue;
+      const long long waves = ceil_div(mpairs * (p.Cout / cand), ncl);
+      const long long cost = waves * (cand == 256 ? 132 : cand == 192 ? 106 : cand == 128 ? 96 : 80);
+      if (best < 0 || cost < best) { best = cost; BN = cand; }      // ties keep the wider tile
+    }
+  }
   pl->bn_tile = BN;
   std::vector<KEnt3> tab;
   int kofs = 0;

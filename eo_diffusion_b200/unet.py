@@ -272,6 +272,7 @@ class UNetModel(nn.Module):
         self._params_flat = None   # cached list(self.parameters()) for the per-forward staleness check
         self._tt_n = 0             # timestep-table size requested by an open `time_tables` block
         self._tt_installed = 0     # size of the table the engine currently holds
+        self._tt_on = False        # ... and whether forwards are using it
 
     # ------------------------------------------------------------------ engine plumbing
     def __getstate__(self):
@@ -285,6 +286,7 @@ class UNetModel(nn.Module):
         state["_params_flat"] = None
         state["_tt_n"] = 0
         state["_tt_installed"] = 0
+        state["_tt_on"] = False
         return state
 
     @property
@@ -384,6 +386,7 @@ class UNetModel(nn.Module):
         self._staged = []   # the engine has packed / copied everything it needs
         self._plan_key = (key, max_batch)
         self._tt_installed = 0   # timestep tables die with the plan
+        self._tt_on = False
 
     @contextlib.contextmanager
     def time_tables(self, n_timesteps: int):
@@ -398,9 +401,9 @@ class UNetModel(nn.Module):
             yield self
         finally:
             self._tt_n = prev
-            if prev == 0 and self._tt_installed and self._handle is not None:
+            if prev == 0 and self._tt_on and self._handle is not None:
                 _lib.check(_lib.lib().eo_unet_clear_time_tables(C.c_void_p(self._handle)), "eo_unet_clear_time_tables")
-                self._tt_installed = 0
+                self._tt_on = False
 
     def launches_per_forward(self) -> int:
         return int(_lib.lib().eo_unet_launches_per_forward(self._ensure_handle()))
@@ -440,10 +443,12 @@ class UNetModel(nn.Module):
             assert y.shape == (B,), (y.shape, x.shape)
         with torch.cuda.device(dev):
             self._plan(dev, B, H, W)
-            if self._tt_n and y is None and self._tt_installed < self._tt_n:
+            if self._tt_n and y is None and (not self._tt_on or self._tt_installed < self._tt_n):
+                # (a table of at least this size kept by the handle from an earlier loop is only switched back on)
                 _lib.check(_lib.lib().eo_unet_build_time_tables(C.c_void_p(self._handle), self._tt_n, _lib.stream_ptr()),
                            "eo_unet_build_time_tables")
-                self._tt_installed = self._tt_n
+                self._tt_installed = max(self._tt_installed, self._tt_n)
+                self._tt_on = True
             xf = x.detach().to(torch.float32).contiguous()
             cf = None if cond is None else cond.detach().to(torch.float32).contiguous()
             ts = timesteps.to(device=dev, dtype=torch.int64).contiguous()

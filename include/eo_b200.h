@@ -122,8 +122,10 @@ EO_API int eo_unet_forward(eo_unet* u, const float* x, int Cx, const float* cond
  * bit-identical to it).  While a table is installed, eo_unet_forward with y == NULL gathers row timesteps[b] (one launch
  * instead of four); a timestep outside [0, n_timesteps) then yields NaN eps, so a sampler installs the table of ITS
  * schedule (EODiffusion: n_timesteps = self.timesteps) and clears it afterwards.  Class-conditional forwards
- * (y != NULL) keep the per-step path: label_emb(y) enters before the projections (:764-766).  A table dies with the
- * plan (eo_unet_finalize).  Synchronises `stream` once. */
+ * (y != NULL) keep the per-step path: label_emb(y) enters before the projections (:764-766).  Building synchronises
+ * `stream` once; a later call with n_timesteps <= the built size only switches the table back on.
+ * eo_unet_clear_time_tables switches it off (forwards take the per-step path again); the memory stays with the handle
+ * until the next eo_unet_finalize / eo_unet_destroy, because row t depends on t alone and stays valid. */
 EO_API int eo_unet_build_time_tables(eo_unet* u, int n_timesteps, void* stream);
 EO_API int eo_unet_clear_time_tables(eo_unet* u);
 
