@@ -1,4 +1,5 @@
-"""Development tool: per-CTA clock totals of the attention kernel on a B200 (eo_debug_conv_trace).
+"""Development tool: per-CTA clock totals of the attention kernel on a B200 (eo_debug_conv_trace; needs a -DEO_DEVTOOLS
+build: EO_LIB_VARIANT=dev EO_NVCC_EXTRA=-DEO_DEVTOOLS python -m eo_diffusion_b200.build, then EO_B200_LIB=.../libeo_b200_dev.so).
 usage: python tools/attn_trace.py [B T heads ch]"""
 import os
 import sys
@@ -30,14 +31,9 @@ def run(B, T, heads, ch):
     nb = np.median(t[:, 7])
     life = np.median(t[:, 0])
     f = lambda c: np.median(t[:, c]) / nb
-    if os.environ.get("EO_ATTN_V4"):
-        print(f"attention(v4) B={B} T={T} heads={heads} ch={ch}: {len(t)} CTAs traced, {nb:.0f} half-blocks, CTA life {life:.0f} clk "
-              f"= {life / nb:.0f} clk per 64 keys\n   per 64 keys: softmax(tile 0) waits S {f(1):.0f}, waits PV {f(2):.0f}, exp pass {f(3):.0f} "
-              f"(redone blocks per CTA {np.median(t[:, 4]):.1f}); MMA warp waits P {f(5):.0f}, waits K/V {f(6):.0f}")
-    else:
-        print(f"attention B={B} T={T} heads={heads} ch={ch}: {len(t)} CTAs traced, {nb:.0f} half-blocks, CTA life {life:.0f} clk "
-              f"= {life / nb:.0f} clk per 64 keys\n   per 64 keys, softmax warp (tile 0): waits S {f(1):.0f}, wait::ld+max(next) {f(2):.0f}, vote(+raise) {f(3):.0f}, "
-              f"exp+pack {f(4):.0f}, st+hand-over {f(5):.0f}; issuer 0 waits P {f(6):.0f}")
+    print(f"attention B={B} T={T} heads={heads} ch={ch}: {len(t)} CTAs traced, {nb:.0f} half-blocks, CTA life {life:.0f} clk "
+          f"= {life / nb:.0f} clk per 64 keys\n   per 64 keys, softmax warp (tile 0): waits S {f(1):.0f}, wait::ld+max(next) {f(2):.0f}, vote(+raise) {f(3):.0f}, "
+          f"exp+pack {f(4):.0f}, st+hand-over {f(5):.0f}; issuer 0 waits P {f(6):.0f}")
 
 if __name__ == "__main__":
     if len(sys.argv) > 4:

@@ -2,6 +2,7 @@
 Slots (eo_debug_conv_trace): 0 lifetime, 1 MMA warp waits on operands, 2 MMA warp waits on a free accumulator
 (= the epilogue is behind), 3 epilogue waits on the accumulator (= the main loop is behind), 4 epilogue busy,
 5 producer waits on free stages, 6 tiles, 7 transform warps busy.  All in clk, printed per tile.
+(the trace / EO_TEST_* switches need a -DEO_DEVTOOLS build loaded through EO_B200_LIB)
 usage: [EO_TEST_GN=2] [EO_TEST_STATS=1] python tools/conv3_trace.py [B H W Cin Cout k res]"""
 import math
 import sys

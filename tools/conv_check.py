@@ -1,6 +1,7 @@
 """Development tool: the tensor-core convolution (C-ABI self-test entry) against torch conv2d on the
 same bf16-rounded operands, over shapes of the BASELINE UNet, plus a per-CTA counter summary of the
-persistent kernel (eo_debug_conv_trace).  usage: python tools/conv_check.py [trace]"""
+persistent kernel (eo_debug_conv_trace).  (the trace / EO_TEST_* switches need a -DEO_DEVTOOLS build loaded through EO_B200_LIB)
+usage: python tools/conv_check.py [trace]"""
 import math
 import os
 import sys

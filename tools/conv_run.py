@@ -1,4 +1,5 @@
 """Development tool: launch one tensor-core convolution a few times (for ncu).
+(the trace / EO_TEST_* switches need a -DEO_DEVTOOLS build loaded through EO_B200_LIB)
 usage: [EO_TEST_GN=2] [EO_TEST_STATS=1] python tools/conv_run.py [B H W Cin Cout k res]"""
 import math
 import sys
