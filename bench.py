@@ -584,7 +584,7 @@ def run_ours(args, wl):
     value = world * B / (steps_per_image * ms_step * 1e-3)
 
     # ---- end to end ---------------------------------------------------------------------------
-    n_e2e = max(args.steps, 50 if B * size * size <= 64 * 256 * 256 else 10)
+    n_e2e = max(args.steps, 100 if B * size * size <= 64 * 256 * 256 else 10)
     if kind == "ddim":
         n_e2e = steps_per_image
     ms_pub, h2d_pub, d2h_pub = e2e_public_sampling(ctx, n_e2e, barrier)
