@@ -46,6 +46,38 @@ const char* get_error();
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol): inside one UNet forward every kernel depends on the one before it, so
+// the chain pays a launch + scheduling gap and a cold prologue (barrier init, TMEM allocation, descriptor prefetch)
+// ~170 times per step.  A kernel launched with the programmatic-serialization attribute may become resident while its
+// predecessor is still running (as SM resources free up), runs its prologue, and blocks in pdl_wait() until the
+// predecessor has COMPLETED and its writes are visible -- nothing a kernel reads or writes is touched before pdl_wait().
+// pdl_trigger() (right after the wait, so at most one generation of waiting kernels exists) lets the NEXT kernel do the
+// same.  Both are no-ops in a kernel launched the ordinary way.
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+// set by the engine around the ops of a forward: true when the previous operation enqueued on the stream was one of
+// this library's kernels (a programmatic edge needs a kernel on both ends); thread-local like the handles' use
+bool pdl_allowed();
+void pdl_set_allowed(bool on);
+
+#ifdef __CUDACC__
+// <<<grid, block, smem, st>>> with the programmatic-serialization attribute when pdl_allowed()
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_allowed() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 int num_sms();  // SM count of the current device (cached)
 
 // SiLU for bf16-bound outputs: x*sigmoid(x) = h + h*tanh(h), h = x/2 -- one MUFU (tanh.approx,

@@ -1330,14 +1330,19 @@ int eo_unet::forward(const float* x, int Cx, const float* cond, int Cc, const in
 int eo_unet::run_ops(int B, cudaStream_t st) {
   EO_CHECK_CUDA(cudaMemsetAsync(gn_sums, 0, (size_t)std::max(n_gn, 1) * Bmax * 64 * sizeof(double), st));
   if (ch_stats_floats) EO_CHECK_CUDA(cudaMemsetAsync(ch_stats, 0, ch_stats_floats * sizeof(double), st));
+  // the two memsets above are not kernels: the first op launches the ordinary way, every later kernel of the chain may be
+  // scheduled behind its predecessor programmatically (common.cuh)
   for (size_t i = 0; i < ops.size(); ++i) {
+    pdl_set_allowed(i > 0);
     int rc = ops[i].run(B, st);
     if (rc) {
+      pdl_set_allowed(false);
       std::string msg = std::string("op '") + ops[i].name + "': " + get_error();
       set_error("%s", msg.c_str());
       return rc;
     }
   }
+  pdl_set_allowed(false);
   return EO_OK;
 }
 
@@ -1392,6 +1397,13 @@ int eo_unet::forward_graph(const float* x, int Cx, const float* cond, int Cc, co
 // ---------------------------------------------------------------------------------------
 namespace eo {
 static thread_local std::string g_err;
+static thread_local bool g_pdl = false;
+bool pdl_allowed() { return g_pdl; }
+#ifdef EO_NO_PDL      // A/B builds (tools/ab.sh): every launch the ordinary way
+void pdl_set_allowed(bool) { g_pdl = false; }
+#else
+void pdl_set_allowed(bool on) { g_pdl = on; }
+#endif
 void set_error(const char* fmt, ...) {
   char buf[1024];
   va_list ap;

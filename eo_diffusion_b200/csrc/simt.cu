@@ -566,6 +566,7 @@ k_chan_stats(const __nv_bfloat16* __restrict__ x, int C, int HW, int ppc, double
 __global__ void k_gn_finalize_ch(const double* __restrict__ sa, int Ca, const double* __restrict__ sb, int Cb,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, int B,
                                  int HW, float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_wait(); pdl_trigger();
   const int C = Ca + Cb;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
@@ -606,6 +607,7 @@ __global__ void k_gn_finalize(const double* __restrict__ sums, const float* __re
 __global__ void __launch_bounds__(256)
 k_gn_apply(GnSrcs srcs, int HW, int ppc, int Ctot, const float* __restrict__ scale,
            const float* __restrict__ shift, int silu, __nv_bfloat16* __restrict__ dst) {
+  pdl_wait(); pdl_trigger();
   const int tid = threadIdx.x, b = blockIdx.y;
   const int p0 = blockIdx.x * ppc, p1 = min(HW, p0 + ppc);
   int coff = 0;
@@ -705,9 +707,8 @@ int launch_chan_stats(const void* x_bf16, int B, int HW, int C, double* stats, c
 int launch_gn_finalize_ch(const double* sa, int Ca, const double* sb, int Cb, const float* gamma, const float* beta,
                           int B, int HW, float* scale, float* shift, cudaStream_t st) {
   EO_REQUIRE((Ca + Cb) % 32 == 0, EO_ERR_ARG, "gn_finalize_ch: channels %d not divisible by 32", Ca + Cb);
-  k_gn_finalize_ch<<<(unsigned)ceil_div((long long)B * (Ca + Cb), 256), 256, 0, st>>>(sa, Ca, sb, Cb, gamma, beta, B, HW,
-                                                                                     scale, shift);
-  EO_CHECK_LAUNCH();
+  EO_CHECK_CUDA(launch_chain(k_gn_finalize_ch, dim3((unsigned)ceil_div((long long)B * (Ca + Cb), 256)), dim3(256), 0, st, sa, Ca,
+                             sb, Cb, gamma, beta, B, HW, scale, shift));
   return EO_OK;
 }
 
@@ -723,9 +724,8 @@ int launch_gn_apply(const GnSrc* src, int nsrc, int B, int HW, const float* scal
   }
   int ppc = pick_ppc(B, HW);
   dim3 grid((unsigned)ceil_div(HW, ppc), (unsigned)B);
-  k_gn_apply<<<grid, 256, 0, st>>>(s, HW, ppc, Ctot, scale, shift, silu,
-                                   reinterpret_cast<__nv_bfloat16*>(dst));
-  EO_CHECK_LAUNCH();
+  EO_CHECK_CUDA(launch_chain(k_gn_apply, grid, dim3(256), 0, st, s, HW, ppc, Ctot, scale, shift, silu,
+                             reinterpret_cast<__nv_bfloat16*>(dst)));
   return EO_OK;
 }
 
@@ -785,6 +785,7 @@ namespace {
 // pass silently); rows of `ld` floats, ld % 4 == 0
 __global__ void __launch_bounds__(256)
 k_gather_rows(const float4* __restrict__ table, int n, int ld4, const long long* __restrict__ t, float4* __restrict__ out) {
+  pdl_wait(); pdl_trigger();
   const int b = blockIdx.y;
   const long long tv = t[b];
   const bool ok = tv >= 0 && tv < n;
@@ -801,9 +802,8 @@ __global__ void k_iota64(long long* out, int n) {
 int launch_gather_rows(const float* table, int n, int ld, const int64_t* t, int B, float* out, cudaStream_t st) {
   EO_REQUIRE(ld % 4 == 0, EO_ERR_ARG, "gather_rows: row length %d is not a multiple of 4", ld);
   dim3 grid((unsigned)std::min<long long>(ceil_div(ld / 4, 256), 8), (unsigned)B);
-  k_gather_rows<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(table), n, ld / 4,
-                                      reinterpret_cast<const long long*>(t), reinterpret_cast<float4*>(out));
-  EO_CHECK_LAUNCH();
+  EO_CHECK_CUDA(launch_chain(k_gather_rows, grid, dim3(256), 0, st, reinterpret_cast<const float4*>(table), n, ld / 4,
+                             reinterpret_cast<const long long*>(t), reinterpret_cast<float4*>(out)));
   return EO_OK;
 }
 

@@ -204,6 +204,8 @@ k_attn_tc5(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  pdl_wait();            // the qkv convolution may still have been running while this CTA set itself up (common.cuh)
+  pdl_trigger();
 
   // 768 threads leave 80 registers each: the issue warpgroup drops to 40, the loader's to 24, the four softmax
   // warpgroups grow to 104 (40 + 24 + 4 * 104 = 480 = 6 * 80)
@@ -465,8 +467,8 @@ int tc_attn_launch(const TcAttnPlan* pl, int B, cudaStream_t st) {
 #else
   auto kern = p.ones_col ? k_attn_tc5<false, true> : k_attn_tc5<false, false>;
 #endif
-  kern<<<grid, ATTN5_THREADS, ATTN5_SMEM, st>>>(pl->map, out, p.T, p.heads, p.ch, scale_log2, g_attn_trace, g_attn_trace_n);
-  EO_CHECK_LAUNCH();
+  EO_CHECK_CUDA(launch_chain(kern, grid, dim3(ATTN5_THREADS), ATTN5_SMEM, st, pl->map, out, p.T, p.heads, p.ch, scale_log2,
+                             g_attn_trace, g_attn_trace_n));
   return EO_OK;
 }
 

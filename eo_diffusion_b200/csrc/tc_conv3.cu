@@ -193,6 +193,10 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   tc::cluster_sync_all();                    // peer barriers are initialised past here
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // everything above touched only this launch's own constants (operand tables, tensor maps) and on-chip state: the CTA
+  // may have been scheduled while the previous kernel of the forward was still running (common.cuh)
+  pdl_wait();
+  pdl_trigger();
 
   // 640 threads leave 96 registers each (61440 for the CTA); the epilogue warps need more and the issue
   // warps far fewer: warpgroup 0 drops to 40, the epilogue warpgroups grow to 104, the transform warpgroups
@@ -966,10 +970,12 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st, float* out_nch
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = (size_t)dyn;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_allowed() ? 2 : 1;
 #ifdef EO_DEVTOOLS
   auto kern = g_trace3 ? k_conv_tc3<true> : k_conv_tc3<false>;
 #else
