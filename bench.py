@@ -10,9 +10,10 @@ posterior update + next step's 'sum' conditioning mix.  images/sec = images in f
 
   value        steps timed on the device (CUDA events) with every input resident in HBM
   e2e          the reference's own call, `EODiffusion.sampling(n, device=..., cond=<host tensor>)` followed by
-               `.cpu()`, on a short-T instance of the same model (the UNet cost per step does not depend on T):
-               host RNG draw of x_T, host -> device copies of x_T and cond, every per-step launch of the public
-               loop and the device -> host read of the result are inside the timed region
+               `.cpu()`: ONE full T = 1000 trajectory of the whole per-GPU batch when that takes <= 90 s (else, or with
+               --short-e2e, a --steps-long instance of the same model); host RNG draw of x_T, host -> device copies
+               of x_T and cond, every per-step launch of the public loop and the device -> host read of the result
+               are inside the timed region
   e2e_streamed the per-step entry points (public methods) fed from pinned host buffers with the copies of step
                k+1 overlapping the compute of step k (what a streaming caller can reach)
   roofline     the dominant kernel family (tcgen05 implicit-GEMM conv), timed live with CUDA events per op
@@ -584,7 +585,8 @@ def run_ours(args, wl):
     value = world * B / (steps_per_image * ms_step * 1e-3)
 
     # ---- end to end ---------------------------------------------------------------------------
-    n_e2e = max(args.steps, 100 if B * size * size <= 64 * 256 * 256 else 10)
+    # the literal metric when it fits in ~1.5 min: one full T = 1000 call of the public sampler; else a shorter instance
+    n_e2e = T_DDPM if ms_step * T_DDPM <= 90e3 and not args.short_e2e else max(args.steps, 10)
     if kind == "ddim":
         n_e2e = steps_per_image
     ms_pub, h2d_pub, d2h_pub = e2e_public_sampling(ctx, n_e2e, barrier)
@@ -702,9 +704,10 @@ def run_ours(args, wl):
                              "working set fits L2: numbers are L2-warm"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_pub, "d2h_bytes_per_step": d2h_pub,
                     "ms_per_step": ms_pub, "steps": n_e2e,
-                    "call": "EODiffusion.sampling(n, device, cond=<pinned host tensor>).cpu() on a "
-                            f"{n_e2e}-step instance; x_T drawn on the host like the reference; copies once per call, "
-                            "divided over its steps" if kind != "ddim" else "DDIMSampler.sample(S, ...)[0].cpu()"},
+                    "call": ("EODiffusion.sampling(n, device, cond=<pinned host tensor>).cpu(), one call of "
+                             f"{n_e2e} steps" + (" = the full T = 1000 trajectory" if n_e2e == T_DDPM else "")
+                             + "; x_T drawn on the host like the reference; copies once per call, divided over its steps")
+                            if kind != "ddim" else "DDIMSampler.sample(S, ...)[0].cpu()"},
             "e2e_streamed": {"value": world * B / (steps_per_image * ms_str * 1e-3), "unit": UNIT,
                              "h2d_bytes_per_step": h2d_str, "d2h_bytes_per_step": d2h_str, "ms_per_step": ms_str},
             "gpu_launches": launches_step * args.steps,
@@ -730,6 +733,7 @@ def main():
     ap.add_argument("--breakdown", default="", help="write the per-op timing JSON here")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the c1/c2/c4/c5 block of the default line")
+    ap.add_argument("--short-e2e", action="store_true", help="time a --steps-long sampling() call instead of the full T = 1000 one")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                    # timing rule: at least 3 warm-up steps

@@ -7,7 +7,7 @@ for round in 1 2; do
   for v in "$@"; do
     lib=eo_diffusion_b200/libeo_b200.so
     [ "$v" != "base" ] && lib=eo_diffusion_b200/libeo_b200_$v.so
-    EO_B200_LIB=$PWD/$lib timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-secondary \
+    EO_B200_LIB=$PWD/$lib timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-secondary --short-e2e \
       --breakdown gpurun_out/bd_${TAG}_${v}_$round.json > gpurun_out/ab_${TAG}_${v}_$round.json 2> gpurun_out/ab_${TAG}_${v}_$round.err
     python - <<PY
 import json

@@ -10,7 +10,7 @@ print("$w", "ms/step %.3f" % d["ms_per_step"], "e2e %.3f" % d["e2e"]["ms_per_ste
 PY
 done
 for r in 1 2; do
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-secondary > gpurun_out/bench_pdl_c3_$r.json 2> gpurun_out/bench_pdl_c3_$r.err
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-secondary --short-e2e > gpurun_out/bench_pdl_c3_$r.json 2> gpurun_out/bench_pdl_c3_$r.err
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/bench_pdl_c3_$r.json").read().strip().splitlines()[-1])
