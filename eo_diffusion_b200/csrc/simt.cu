@@ -982,8 +982,12 @@ int launch_attention_wide_t(const TIO* qkv, TIO* out, int B, int T, int heads, i
   dim3 grid((unsigned)ceil_div(T, AW_WARPS), (unsigned)heads, (unsigned)B);
 #define EO_AW(NCV)                                                                                                  \
   do {                                                                                                              \
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attention_wide<TIO, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                       64 * 1024));                                                                 \
+    static bool attr_set = false;       /* once per instantiation, outside any stream capture that follows */      \
+    if (!attr_set) {                                                                                                \
+      EO_CHECK_CUDA(cudaFuncSetAttribute(k_attention_wide<TIO, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         64 * 1024));                                                               \
+      attr_set = true;                                                                                              \
+    }                                                                                                               \
     k_attention_wide<TIO, NCV><<<grid, AW_WARPS * 32, smem, st>>>(qkv, out, T, heads, ch, ld, head_stride,         \
                                                                    part_stride, scale, KT);                         \
   } while (0)

@@ -57,6 +57,10 @@ def test_eps_at_benchmarked_geometries(cuda_dev, name, mode):
     print(f"[parity] {mode} {name}: eps rel L2 {err:.3e}")
     tol = TOL[mode] if (mode == "fp32" or cfg["model_channels"] >= 128) else TOL_BF16_NARROW
     assert err <= tol, f"{name} {mode}: rel L2 {err:.3e} > {tol}"
+    # the second call is captured into a CUDA graph, the third replays it: same bits
+    xd, td = x.to(cuda_dev), tt(g["t"]).to(cuda_dev)
+    cd = None if cond is None else cond.to(cuda_dev)
+    assert torch.equal(m(xd, td, cond=cd), eps) and torch.equal(m(xd, td, cond=cd), eps)
     _models.pop((json.dumps(cfg, sort_keys=True), mode), None)      # the 256 x 256 plan holds ~1 GB; free it
     gc.collect()
 
