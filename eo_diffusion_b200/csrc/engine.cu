@@ -1674,6 +1674,25 @@ int eo_test_attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int
   TcAttnPlan* plan = nullptr;
   rc = tc_attn_plan_create(p, &plan);
   if (!rc) rc = tc_attn_launch(plan, B, st);
+#ifdef EO_DEVTOOLS
+  if (!rc) {     // development builds: the kernel alone, best of three (stderr)
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int i = 0; i < 3 && !rc; ++i) {
+      cudaEventRecord(e0, st);
+      rc = tc_attn_launch(plan, B, st);
+      cudaEventRecord(e1, st);
+      cudaEventSynchronize(e1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      best = ms < best ? ms : best;
+    }
+    fprintf(stderr, "[eo devtools] attention kernel B=%d T=%d heads=%d ch=%d: %.4f ms, %.1f TFLOP/s algorithmic\n", B, T, heads, ch,
+            best, 4.0 * B * heads * (double)T * T * ch / best / 1e9);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+#endif
   cudaError_t e = cudaStreamSynchronize(st);
   tc_attn_plan_destroy(plan);
   cudaFree(padded);

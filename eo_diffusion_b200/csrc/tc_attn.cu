@@ -14,6 +14,7 @@
 #include "kernels.h"
 #include "tc_common.cuh"
 #include <cstdlib>
+#include <type_traits>
 
 namespace eo {
 
@@ -415,6 +416,425 @@ k_attn_tc5(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
   if (trc && threadIdx.x == 0) trc[0] = clock64() - t_entry;
 }
 
+
+// =====================================================================================================
+// k_attn_tc6: k_attn_tc5's four tiles and 32-key quarter-blocks with the hand-offs taken off the critical path.
+//
+// A clock64 timeline of k_attn_tc5 (tools/attn_timeline.py) showed its four tiles running in LOCKSTEP: every softmax
+// warp of a scheduler sat in the same phase at the same time (all four queueing for the MUFU pipe, then all four in the
+// barrier wait / tcgen05.ld / maximum / vote with the MUFU pipe idle), and then all four issuers pushed their five MMAs
+// into the one tensor pipe at once (736 clk per round, the S MMA at N = 32 costs 40 clk for 16 clk of work because it
+// re-reads Q from shared memory) while every softmax warp waited for S.  Here
+//   * the softmax is software-pipelined across quarter-blocks: the row of S_q+1 is fetched into a second register set
+//     behind the first half of the exponentials of S_q (tcgen05.ld is asynchronous until its registers are read), its
+//     maximum and the raise vote are taken after P_q has been handed over -- a warp's instruction stream has MUFU work
+//     nearly all the time and never waits on a barrier that has not long completed;
+//   * S has ONE 32-column buffer per tile, released when its row is in registers (s_free) instead of when P has been
+//     consumed, and P a buffer of its own: S_q+2 is issued half a round earlier than before;
+//   * TSQ (head dimension <= 48, the T = 4096 blocks): the softmax threads copy their Q row into tensor memory once, so
+//     S = Q K^T is a TS MMA (16 clk per K step instead of 40) and O is only round16(ch) columns wide: tensor time per
+//     round and tile 48 + 48 instead of 120 + 64 clk.  Wider heads keep Q in shared memory and a 64-column O.
+// Tensor memory per tile (128 columns): S 0..31, P 32..47 (packed bf16 pairs), O 48..48+ON, Q 96..96+ON/2 (TSQ).
+// Barriers per tile: s_full (commit of S_q), s_free (128 threads: row read), p_full (128 threads: P_q written), pv_done (commit
+// of P V_q; the softmax waits for P V_q-1 before it overwrites P or rescales O), q_ready (4 warps: Q copied).
+// The row sum l is accumulated by the softmax threads (packed fp32 adds).
+// =====================================================================================================
+constexpr int OFF6_BAR = OFF5_BAR;
+// q_full, kv_full[S], kv_empty[S], then per tile: s_full, s_free, p_full, pv_done, q_ready
+constexpr int N_BARS6 = 1 + 2 * KV_STAGES5 + 5 * NT5;
+constexpr int ATTN6_SMEM = OFF6_BAR + N_BARS6 * 8 + 16 + 1024;
+constexpr int TM6_S = 0, TM6_P = 32, TM6_O = 48, TM6_Q = 96;
+
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t v[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
+// wait without the trap counter of tc::mbar_wait: the single issuer thread competes with four softmax warps for its
+// scheduler's issue slots, every instruction in its loop counts
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}"
+      :: "r"(tc::smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <bool TRACE, int ON>      // ON: columns of O = round16(ch); Q in tensor memory below 64
+__global__ void __launch_bounds__(ATTN5_THREADS, 1)
+k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out, int T,
+           int heads, int ch, float scale_log2, long long* trace, int trace_n) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF6_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + KV_STAGES5;
+  uint64_t* s_full = kv_empty + KV_STAGES5;   // [tile]
+  uint64_t* s_free = s_full + NT5;
+  uint64_t* p_full = s_free + NT5;
+  uint64_t* pv_done = p_full + NT5;
+  uint64_t* q_ready = pv_done + NT5;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_ready + NT5);
+
+  // warp index through a shuffle: the compiler then knows it (and the tile, quadrant, barrier and tensor-memory
+  // addresses derived from it) to be warp-uniform and keeps them in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const long long t_entry = TRACE ? clock64() : 0;
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  long long* trc = (TRACE && cta_lin < trace_n) ? trace + (long long)cta_lin * 8 : nullptr;
+  // timeline (TRACE only): rows behind the per-CTA totals, CTA TL_CTA, rounds TL_Q0 .. TL_Q0 + 15: softmax warps
+  // [tile][quadrant][round][8] = loop top, first half done, next row requested, second half done, next row there,
+  // P V_q-1 seen, P handed over, next maximum known; then issuers
+  // [tile][round][4] = round starts, next S issued, saw P, P V issued
+  constexpr int TL_CTA = 150, TL_Q0 = 48, TL_N = 16;
+  long long* tl = (TRACE && cta_lin == TL_CTA && trace_n > TL_CTA) ? trace + (long long)trace_n * 8 : nullptr;
+  const int q0 = blockIdx.x * NT5 * QT, h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = min(NT5, (T - q0 + QT - 1) / QT);
+  const int nblk = (T + KT - 1) / KT;
+  const int nq = (T + KQ5 - 1) / KQ5;          // quarter-blocks that hold at least one key
+  const int cq = h * 3 * HD, ck = cq + HD, cv = cq + 2 * HD;
+  constexpr bool TSQ = ON < HD;
+  constexpr int on = ON;
+  constexpr int ksteps = ON / 16;                 // the padded channels of q and k are zero
+
+  if (warp == 4 && lane == 0) {
+    tc::tma_prefetch_desc(&map_qkv);
+    tc::mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES5; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], ntiles); }
+    for (int i = 0; i < NT5; ++i) {
+      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_free[i], 128); tc::mbar_init(&p_full[i], 128);
+      tc::mbar_init(&pv_done[i], 1); tc::mbar_init(&q_ready[i], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) { tc::tmem_alloc(tmem_ptr, TM_COLS); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  pdl_wait();            // the qkv convolution may still have been running while this CTA set itself up (common.cuh)
+  pdl_trigger();
+
+  // 768 threads leave 80 registers each: the issue warpgroup drops to 40, the loader's to 24, the four softmax
+  // warpgroups grow to 104 (40 + 24 + 4 * 104 = 480 = 6 * 80; the pool is what the CTA was launched with)
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    // ---------------------------------------------------------------- MMA issuer of tile `warp`: ONE thread runs the
+    // whole loop.  The issuer shares its scheduler with four busy softmax warps and gets every fifth issue slot at
+    // best, so what bounds a round is how many instructions the issuer needs per quarter-block (tools/attn_timeline.py:
+    // the rolled loop of k_attn_tc5 took 500-700 clk to get five MMAs out).  Unrolled over the four K/V stages and the
+    // four quarter-blocks of a tile every descriptor is a constant offset from one base and every parity a constant.
+    if (warp < ntiles && tc::elect_one()) {
+      const int t = warp;
+      constexpr uint32_t idesc_s = tc::make_idesc_bf16(128, KQ5, 0, 0);  // Q (K-major / tensor memory) x K (K-major)
+      constexpr uint32_t idesc_o = tc::make_idesc_bf16(128, on, 0, 1);   // P (tensor memory) x V (MN-major)
+      constexpr uint32_t TILE16 = TILE_BYTES >> 4, QUART16 = (KQ5 * 128) >> 4;
+      const uint64_t qdesc = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_Q)) + (uint64_t)(t * TILE16);
+      const uint64_t kd0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_K));
+      const uint64_t vd0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_V));
+      const uint32_t tb = tmem + t * 128;
+      // S = Q_t K^T for the quarter-block whose K rows start at descriptor `kd`
+      auto issue_s = [&](uint64_t kd) {
+#pragma unroll
+        for (int k = 0; k < ksteps; ++k) {
+          if (TSQ) umma_f16_ts(tb + TM6_S, tb + TM6_Q + k * 8, kd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          else tc::umma_f16_ss(tb + TM6_S, qdesc + 2 * k, kd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(&s_full[t]);
+      };
+      long long tr_p = 0;
+      if (TSQ) mbar_wait_lean(&q_ready[t], 0); else mbar_wait_lean(q_full, 0);
+      mbar_wait_lean(&kv_full[0], 0);
+      tc::tc_fence_after();
+      issue_s(kd0);
+      if (nq > 1) {                     // S_1 as soon as the row of S_0 is in registers
+        mbar_wait_lean(&s_free[t], 0);
+        tc::tc_fence_after();
+        issue_s(kd0 + (uint64_t)QUART16);
+      }
+      // Round q: S_q+2 first (s_free(q + 1) arrives a little before p_full(q), and S is what the softmax waits for
+      // next), then P V_q (which only has to complete before P_q+1 is written, a whole round later)
+      uint32_t st = 0, kvph = 0;        // stage of K/V tile `blk`, phase of kv_full for this pass over the stages
+      uint64_t kd = kd0, vd = vd0;      // descriptors of K/V tile `blk`
+      for (int blk = 0; blk < nblk; ++blk) {
+        // stage / phase / descriptors of K/V tile blk + 1
+        const uint32_t st1 = (st + 1 == KV_STAGES5) ? 0u : st + 1;
+        const uint32_t ph1 = (st + 1 == KV_STAGES5) ? (kvph ^ 1) : kvph;
+        const uint64_t kd1 = kd0 + (uint64_t)(st1 * TILE16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int q = blk * 4 + j;
+          if (q >= nq) break;
+          long long* tli = (TRACE && tl && q >= TL_Q0 && q < TL_Q0 + TL_N) ? tl + 16 * TL_N * 8 + ((t * TL_N) + q - TL_Q0) * 4 : nullptr;
+          if (TRACE && tli) tli[0] = clock64();
+          if (q + 2 < nq) {
+            if (j == 2) mbar_wait_lean(&kv_full[st1], ph1);      // quarter-block q + 2 opens K/V tile blk + 1
+            mbar_wait_lean(&s_free[t], (j + 1) & 1);
+            tc::tc_fence_after();
+            issue_s(j >= 2 ? kd1 + (uint64_t)((j - 2) * QUART16) : kd + (uint64_t)((j + 2) * QUART16));
+          }
+          if (TRACE && tli) tli[1] = clock64();
+          { ATR_T0(); mbar_wait_lean(&p_full[t], j & 1); ATR_ACC(tr_p); }
+          tc::tc_fence_after();
+          if (TRACE && tli) tli[2] = clock64();
+          // O_t (+)= P_q V_q; A: 16 keys = 8 packed columns of P; B: 16 rows of 128 B of V
+          umma_f16_ts(tb + TM6_O, tb + TM6_P, vd + (uint64_t)(j * QUART16), idesc_o, q != 0 ? 1u : 0u);
+          umma_f16_ts(tb + TM6_O, tb + TM6_P + 8, vd + (uint64_t)(j * QUART16 + (16 * 128 >> 4)), idesc_o, 1u);
+          tc::umma_commit(&pv_done[t]);
+          if (j == 3 || q == nq - 1) tc::umma_commit(&kv_empty[st]);
+          if (TRACE && tli) tli[3] = clock64();
+        }
+        st = st1; kvph = ph1; kd = kd1; vd = vd0 + (uint64_t)(st1 * TILE16);
+      }
+      if (trc && warp == 0) { trc[6] = tr_p; trc[7] = (nq + 1) / 2; }
+    }
+    __syncwarp();
+  } else if (warp < SM_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    // ---------------------------------------------------------------- TMA loader (warp 4)
+    if (warp == 4) {
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(q_full, ntiles * TILE_BYTES);
+        for (int t = 0; t < ntiles; ++t)
+          tc::tma_load_3d(smem + OFF5_Q + t * TILE_BYTES, &map_qkv, q_full, cq, q0 + t * QT, b);
+      }
+      __syncwarp();
+      uint32_t s = 0, ph = 0;
+      for (int j = 0; j < nblk; ++j) {
+        tc::mbar_wait(&kv_empty[s], ph ^ 1);
+        if (tc::elect_one()) {
+          tc::mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+          tc::tma_load_3d(smem + OFF5_K + s * TILE_BYTES, &map_qkv, &kv_full[s], ck, j * KT, b);
+          tc::tma_load_3d(smem + OFF5_V + s * TILE_BYTES, &map_qkv, &kv_full[s], cv, j * KT, b);
+        }
+        __syncwarp();
+        if (++s == KV_STAGES5) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ---------------------------------------------------------------- softmax / output: thread <-> query row
+    const int t = (warp - SM_WARP0) >> 2;
+    if (t < ntiles) {
+      const int qd = warp & 3;
+      const int row = qd * 32 + lane;
+      const uint32_t tb = tmem + ((uint32_t)(qd * 32) << 16) + t * 128;
+      const uint32_t sa = tb + TM6_S, pa = tb + TM6_P, oa = tb + TM6_O;
+      float m = -INFINITY;                   // integer-valued reference maximum (log2 domain)
+      uint64_t l2 = pack2(0.f, 0.f);         // row sum, two partial sums
+      long long tr_s = 0;
+      const uint64_t sc2 = pack2(scale_log2, scale_log2);
+
+      if (TSQ) {
+        // this thread's Q row, shared memory (128-byte rows, 16-byte chunk j of row r at position j ^ (r & 7)) ->
+        // tensor memory, 8 packed columns per K step of 16 channels
+        tc::mbar_wait(q_full, 0);
+        const uint8_t* qrow = smem + OFF5_Q + t * TILE_BYTES + row * 128;
+#pragma unroll
+        for (int k = 0; k < ksteps; ++k) {
+          uint32_t w[8];
+          const uint4 c0 = *reinterpret_cast<const uint4*>(qrow + (((2 * k) ^ (row & 7)) << 4));
+          const uint4 c1 = *reinterpret_cast<const uint4*>(qrow + (((2 * k + 1) ^ (row & 7)) << 4));
+          w[0] = c0.x; w[1] = c0.y; w[2] = c0.z; w[3] = c0.w; w[4] = c1.x; w[5] = c1.y; w[6] = c1.z; w[7] = c1.w;
+          tmem_st_32x8(tb + TM6_Q + k * 8, w);
+        }
+        tmem_st_wait();
+        tc::tc_fence_before();
+        if (tc::elect_one()) tc::mbar_arrive(&q_ready[t]);
+      }
+
+      // the four barriers of this tile through ONE opaque base register (s_full + 0, s_free + 32, p_full + 64,
+      // pv_done + 96 bytes): the compiler would otherwise re-derive every address from the warp index at every use
+      uint32_t bar_t = tc::smem_u32(&s_full[t]);
+      asm volatile("mov.u32 %0, %0;" : "+r"(bar_t));
+      constexpr int B_SFULL = 0, B_SFREE = NT5 * 8, B_PFULL = 2 * NT5 * 8, B_PVDONE = 3 * NT5 * 8;
+      // one non-blocking test (its latency overlaps the arithmetic that follows), then a spin only if it failed
+      auto bar_test = [&](int off, uint32_t parity) -> uint32_t {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar_t + off), "r"(parity) : "memory");
+        return ok;
+      };
+      auto bar_spin = [&](int off, uint32_t parity) {
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+                     :: "r"(bar_t + off), "r"(parity) : "memory");
+      };
+      // every lane arrives (128 per tile): one instruction, where electing a lane costs five (measured: 3 % of the kernel)
+      auto bar_arrive = [&](int off) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar_t + off) : "memory");
+      };
+
+      // scaled row maximum of a quarter-block (MASK: keys beyond T set to -inf in the registers)
+      auto row_max = [&](uint32_t (&r)[32], int nvalid) -> float {
+        if (nvalid < KQ5) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= nvalid) r[i] = 0xff800000u;   // -inf
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          mx[(i >> 1) & 3] = max3(mx[(i >> 1) & 3], __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2;
+      };
+      // pairs k0 .. k1 - 1 of P = 2^(S * scale - m), rounded to bf16 pairs; their sum into l2
+      auto exps = [&](const uint32_t (&r)[32], uint32_t (&pk)[16], auto k0c, auto k1c, uint64_t nm2) {
+        constexpr int k0 = decltype(k0c)::value, k1 = decltype(k1c)::value;
+#pragma unroll
+        for (int k = k0; k < k1; ++k) {
+          const uint64_t x = fma2(pack2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1])), sc2, nm2);
+          const bool on_fma = POLY_NUM > 0 && ((k * POLY_NUM) % POLY_DEN) < POLY_NUM;
+          float p0, p1;
+          if (on_fma) {
+            ex2_fma2(x, p0, p1);
+          } else {
+            float x0, x1;
+            unpack2(x, x0, x1);
+            p0 = ex2(x0); p1 = ex2(x1);
+          }
+          l2 = add2(l2, pack2(p0, p1));
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+          pk[k] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+      };
+      float cm;
+      bool raise;
+      // Quarter-block q: `v` = its logits, `cm` their scaled row maximum, `raise` the vote (all taken during q - 1).
+      // The four softmax warps of a scheduler run in lockstep (same code, same data rates), so nothing but this warp's
+      // own arithmetic can cover the latency of a barrier test, tcgen05.ld or tcgen05.st: each is issued early and its
+      // result used late.  LAST: no quarter-block q + 1; MASK: quarter-block q + 1 may hold keys beyond T.
+      auto round = [&](int q, uint32_t (&v)[32], uint32_t (&vn)[32], auto last_c, auto mask_c) {
+        constexpr bool LAST = decltype(last_c)::value, MASK = decltype(mask_c)::value;
+        long long* tlq = (TRACE && tl && lane == 0 && q >= TL_Q0 && q < TL_Q0 + TL_N) ? tl + (((t * 4 + qd) * TL_N) + q - TL_Q0) * 8 : nullptr;
+        if (TRACE && tlq) tlq[0] = clock64();
+        bool pv_seen = q == 0;          // P V_q-1 known complete
+        if (raise) {
+          // raise the reference maximum: O and l scale by the exact power of two 2^(m_old - m_new)
+          const float m_new = fmaxf(m, ceilf(cm));
+          const float alpha = (m_new == m) ? 1.0f : ex2(m - m_new);     // first quarter-block: ex2(-inf) = 0
+          m = m_new;
+          l2 = fma2(l2, pack2(alpha, alpha), pack2(0.f, 0.f));
+          if (q > 0) {
+            bar_spin(B_PVDONE, (q - 1) & 1);
+            pv_seen = true;
+            tc::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < on; c += 16) {
+              uint32_t o[16];
+              tmem_ld_32x16(oa + c, o);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x16(oa + c, o);
+            }
+          }
+        }
+        const uint64_t nm2 = pack2(-m, -m);
+        uint32_t pk[16];
+        using I0 = std::integral_constant<int, 0>; using I6 = std::integral_constant<int, 6>; using I16 = std::integral_constant<int, 16>;
+        uint32_t ok_s = 1;
+        if (!LAST) ok_s = bar_test(B_SFULL, (q + 1) & 1);
+        exps(v, pk, I0{}, I6{}, nm2);
+        if (TRACE && tlq) tlq[1] = clock64();
+        if (!LAST) {
+          if (!ok_s) { ATR_T0(); bar_spin(B_SFULL, (q + 1) & 1); ATR_ACC(tr_s); }
+          tc::tc_fence_after();
+          tc::tmem_ld_32x32(sa, vn);
+        }
+        if (TRACE && tlq) tlq[2] = clock64();
+        uint32_t ok_pv = 1;
+        if (!pv_seen) ok_pv = bar_test(B_PVDONE, (q - 1) & 1);
+        exps(v, pk, I6{}, I16{}, nm2);
+        if (TRACE && tlq) tlq[3] = clock64();
+        if (!ok_pv) bar_spin(B_PVDONE, (q - 1) & 1);       // P V_q-1 has read P
+        if (!pv_seen) tc::tc_fence_after();
+        if (TRACE && tlq) tlq[4] = clock64();
+        tmem_st_32x16(pa, pk);
+        if (!LAST) {
+          tc::tmem_ld_wait();                       // the row of S_q+1 is in registers: S_q+2 may overwrite it
+          tc::tc_fence_before();
+          bar_arrive(B_SFREE);
+        }
+        if (TRACE && tlq) tlq[5] = clock64();
+        if (!LAST) cm = row_max(vn, MASK ? T - (q + 1) * KQ5 : KQ5);     // covers the latency of the tcgen05.st
+        tmem_st_wait();
+        tc::tc_fence_before();
+        bar_arrive(B_PFULL);                        // the warp's tcgen05.st are complete (wait::st is warp-wide)
+        if (TRACE && tlq) tlq[6] = clock64();
+        raise = false;
+        if (!LAST) raise = __any_sync(0xffffffffu, cm > m + RESCALE_THRESHOLD);     // warp-uniform (the TMEM accesses are warp-collective)
+        if (TRACE && tlq) tlq[7] = clock64();
+      };
+
+      uint32_t va[32], vb[32];
+      bar_spin(B_SFULL, 0);
+      tc::tc_fence_after();
+      tc::tmem_ld_32x32(sa, va);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      bar_arrive(B_SFREE);
+      cm = row_max(va, T);
+      raise = true;
+      {
+        using F = std::false_type; using Tr = std::true_type;
+        int q = 0;
+        for (; q + 3 < nq; q += 2) {       // rounds whose successor is not the last quarter-block
+          round(q, va, vb, F{}, F{});
+          round(q + 1, vb, va, F{}, F{});
+        }
+        if (nq - q == 3) {
+          round(q, va, vb, F{}, F{});
+          round(q + 1, vb, va, F{}, Tr{});
+          round(q + 2, va, vb, Tr{}, F{});
+        } else if (nq - q == 2) {
+          round(q, va, vb, F{}, Tr{});
+          round(q + 1, vb, va, Tr{}, F{});
+        } else {
+          round(q, va, vb, Tr{}, F{});
+        }
+      }
+      if (trc && warp == SM_WARP0 && lane == 0) { trc[1] = tr_s; trc[2] = 0; trc[3] = 0; trc[4] = 0; trc[5] = 0; }
+      tc::mbar_wait(&pv_done[t], (nq - 1) & 1);
+      tc::tc_fence_after();
+      const int qi = q0 + t * QT + row;
+      __nv_bfloat16* op = out + ((long long)b * T + qi) * (heads * ch) + h * ch;
+      float l0, l1;
+      unpack2(l2, l0, l1);
+      const float inv = 1.0f / (l0 + l1);
+#pragma unroll 1
+      for (int c = 0; c < on; c += 16) {
+        uint32_t o[16];
+        tmem_ld_32x16(oa + c, o);
+        tc::tmem_ld_wait();
+        if (qi < T) {
+#pragma unroll
+          for (int d = 0; d < 16; d += 8) {
+            if (c + d < ch) {
+              uint4 w4;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                h2[e] = __floats2bfloat162_rn(__uint_as_float(o[d + 2 * e]) * inv,
+                                              __uint_as_float(o[d + 2 * e + 1]) * inv);
+              *reinterpret_cast<uint4*>(op + c + d) = w4;
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, TM_COLS);
+  }
+  if (trc && threadIdx.x == 0) trc[0] = clock64() - t_entry;
+}
+
 long long* g_attn_trace = nullptr;
 int g_attn_trace_n = 0;
 
@@ -445,31 +865,55 @@ int tc_attn_plan_create(const TcAttnParams& p, TcAttnPlan** out) {
 
 void tc_attn_plan_destroy(TcAttnPlan* p) { delete p; }
 
-int tc_attn_launch(const TcAttnPlan* pl, int B, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
-#ifdef EO_DEVTOOLS
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
-#endif
-    attr_set = true;
-  }
+template <bool TRACE>
+static int attn6_launch(const TcAttnPlan* pl, int B, cudaStream_t st, long long* trace, int trace_n) {
   const TcAttnParams& p = pl->p;
   // logits = (q . k) * ch^-1/2 ; softmax evaluated with exp2
   float scale_log2 = (1.0f / sqrtf((float)p.ch)) * 1.4426950408889634f;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
   dim3 grid((unsigned)ceil_div(p.T, NT5 * QT), (unsigned)p.heads, (unsigned)B);
-#ifdef EO_DEVTOOLS
-  auto kern = g_attn_trace ? (p.ones_col ? k_attn_tc5<true, true> : k_attn_tc5<true, false>)
-                           : (p.ones_col ? k_attn_tc5<false, true> : k_attn_tc5<false, false>);
-#else
-  auto kern = p.ones_col ? k_attn_tc5<false, true> : k_attn_tc5<false, false>;
+  static bool attr_set = false;        // per instantiation (TRACE)
+  if (!attr_set) {
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN6_SMEM));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN6_SMEM));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN6_SMEM));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN6_SMEM));
+    attr_set = true;
+  }
+  auto go = [&](auto kern) -> int {
+    EO_CHECK_CUDA(launch_chain(kern, grid, dim3(ATTN5_THREADS), ATTN6_SMEM, st, pl->map, out, p.T, p.heads, p.ch, scale_log2,
+                               trace, trace_n));
+    return EO_OK;
+  };
+  // O is round16(ch) columns wide; below 64 the Q rows live in tensor memory
+  if (p.ch <= 16) return go(k_attn_tc6<TRACE, 16>);
+  if (p.ch <= 32) return go(k_attn_tc6<TRACE, 32>);
+  if (p.ch <= 48) return go(k_attn_tc6<TRACE, 48>);
+  return go(k_attn_tc6<TRACE, 64>);
+}
+
+int tc_attn_launch(const TcAttnPlan* pl, int B, cudaStream_t st) {
+#ifdef EO_ATTN_V5     // A/B builds: the previous kernel
+  {
+    static bool attr5 = false;
+    if (!attr5) {
+      EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
+      EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
+      attr5 = true;
+    }
+    const TcAttnParams& p = pl->p;
+    float scale_log2 = (1.0f / sqrtf((float)p.ch)) * 1.4426950408889634f;
+    dim3 grid((unsigned)ceil_div(p.T, NT5 * QT), (unsigned)p.heads, (unsigned)B);
+    auto kern = p.ones_col ? k_attn_tc5<false, true> : k_attn_tc5<false, false>;
+    EO_CHECK_CUDA(launch_chain(kern, grid, dim3(ATTN5_THREADS), ATTN5_SMEM, st, pl->map, reinterpret_cast<__nv_bfloat16*>(p.out), p.T,
+                               p.heads, p.ch, scale_log2, (long long*)nullptr, 0));
+    return EO_OK;
+  }
 #endif
-  EO_CHECK_CUDA(launch_chain(kern, grid, dim3(ATTN5_THREADS), ATTN5_SMEM, st, pl->map, out, p.T, p.heads, p.ch, scale_log2,
-                             g_attn_trace, g_attn_trace_n));
-  return EO_OK;
+#ifdef EO_DEVTOOLS
+  if (g_attn_trace) return attn6_launch<true>(pl, B, st, g_attn_trace, g_attn_trace_n);
+#endif
+  return attn6_launch<false>(pl, B, st, nullptr, 0);
 }
 
 }  // namespace eo

@@ -7,6 +7,7 @@
 __device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ unsigned ex2h2(unsigned x) { unsigned y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
 
+__device__ __forceinline__ unsigned ex2b2(unsigned x) { unsigned y; asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
 __device__ __forceinline__ float tanh_a(float x) { float y; asm volatile("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_a(float x) { float y; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -29,6 +30,9 @@ __global__ void k(long long* out, float seed, int iters) {
     } else if (MODE == 2) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) h[i] = ex2h2(h[i]);
+    } else if (MODE == 5) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) h[i] = ex2b2(h[i]);
     } else if (MODE == 3) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) a[i] = tanh_a(a[i]);
@@ -59,6 +63,7 @@ int main() {
   for (int w : {1, 2, 4}) run<0>(d, w, "MUFU.EX2 f32", 16);
   for (int w : {1, 2, 4}) run<1>(d, w, "FFMA + MUFU.EX2 + FADD", 16);
   for (int w : {1, 2, 4}) run<2>(d, w, "ex2.f16x2 (2 MUFU.EX2.F16)", 16);
+  for (int w : {1, 2, 4}) run<5>(d, w, "ex2.bf16x2", 16);
   for (int w : {1, 2, 4}) run<3>(d, w, "MUFU.TANH", 16);
   for (int w : {1, 2}) run<4>(d, w, "MUFU.RCP", 16);
   return 0;
