@@ -621,7 +621,7 @@ def run_ours(args, wl):
                     "share_of_unet_time": e["ms"] / total_ms,
                     "whole_step": {"achieved": total_fl / (ms_step * 1e-3) / 1e12,
                                    "frac": total_fl / (ms_step * 1e-3) / 1e12 / peaks["tflops"]}}
-        a = breakdown.get("k_attn_tc5")
+        a = breakdown.get("k_attn_tc6")
         if a:
             attention = {"ms": a["ms"], "share_of_unet_time": a["ms"] / total_ms,
                          "achieved": a["flops"] / (a["ms"] * 1e-3) / 1e12,

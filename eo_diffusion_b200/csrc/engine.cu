@@ -334,6 +334,7 @@ struct eo_unet {
 
   struct PackSeg { const float* wsrc; int cin_total; int ksize; int cin_off; int C; };
   float* last_packed_bias = nullptr;   // bias vector of the conv planned last (plan_attn patches the qkv one)
+  const float* pack_row_scale = nullptr;   // per-output-row factor applied by pack_tc / pack_bias2 while set (device, [rows])
 
   // SIMT layout [Ktot][Cout] fp32
   int pack_simt(const std::vector<PackSeg>& segs, int Cout, float** out, int* ktot, cudaStream_t st) {
@@ -360,7 +361,7 @@ struct eo_unet {
     if (rc) return rc;
     int koff = 0;
     for (auto& s : segs) {
-      rc = launch_pack_conv_weight(s.wsrc, s.cin_total, s.ksize, s.cin_off, s.C, d, DT_BF16, K, 1, koff, Nrows, d_row_map, st);
+      rc = launch_pack_conv_weight(s.wsrc, s.cin_total, s.ksize, s.cin_off, s.C, d, DT_BF16, K, 1, koff, Nrows, d_row_map, st, pack_row_scale);
       if (rc) return rc;
       koff += s.ksize * s.ksize * s.C;
     }
@@ -371,7 +372,7 @@ struct eo_unet {
     float* d = nullptr;
     int rc = dmalloc(&d, (size_t)N);
     if (rc) return rc;
-    rc = launch_pack_bias(a, b, d, N, d_row_map, st);
+    rc = launch_pack_bias(a, b, d, N, d_row_map, st, pack_row_scale);
     if (rc) return rc;
     *out = d;
     return EO_OK;
@@ -851,20 +852,38 @@ struct eo_unet {
       if (rc) return rc;
       EO_CHECK_CUDA(cudaMemcpyAsync(d_rmap, rmap.data(), rows * sizeof(int), cudaMemcpyHostToDevice, st));
       EO_CHECK_CUDA(cudaStreamSynchronize(st));   // rmap is a stack-lifetime host buffer
+      // head dimension <= 48: the logit scale ch^-1/2 (and log2 e: the softmax runs on exp2) is folded into the q rows of
+      // the projection, weights and bias, in fp32 before they are rounded -- the attention kernel gets S * scale out
+      // of the tensor core and q is still rounded to bf16 exactly once
+      const bool k_one = ch <= 48;
+      float* d_rscale = nullptr;
+      if (k_one) {
+        std::vector<float> rs(rows, 1.0f);
+        const float sl2 = (1.0f / sqrtf((float)ch)) * 1.4426950408889634f;
+        for (int h = 0; h < heads; ++h)
+          for (int c2 = 0; c2 < 64; ++c2) rs[(h * 3 + 0) * 64 + c2] = sl2;
+        rc = dmalloc(&d_rscale, (size_t)rows);
+        if (rc) return rc;
+        EO_CHECK_CUDA(cudaMemcpyAsync(d_rscale, rs.data(), rows * sizeof(float), cudaMemcpyHostToDevice, st));
+        EO_CHECK_CUDA(cudaStreamSynchronize(st));   // rs is a stack-lifetime host buffer
+      }
       Act qkv;
+      pack_row_scale = d_rscale;
       rc = plan_conv_tc(p + "qkv", {fuse ? with_gn(seg1x1(x), g, 0, 0) : seg1x1(xn)}, {{wq, C, 1, 0, C}}, rows, d_rmap,
                         w(p + "qkv.bias"), nullptr, -1, nullptr, x.H, x.W, &qkv, st, /*want_stats=*/false, nullptr,
                         /*alg_flops=*/2.0 * x.H * x.W * 3.0 * C * C);
+      pack_row_scale = nullptr;
       if (rc) return rc;
       if (fuse) free_gn(g);
-      // head dimension < 64: padded channel 63 of every head's v becomes 1.0 (zero weight row, bias 1), so the
-      // attention kernel gets the softmax row sums out of its P V product
-      const bool ones_col = ch < 64;
-      if (ones_col) {
+      // ... and the first padded channel behind round16(ch) of every head's k becomes 1.0 (zero weight row, bias 1):
+      // the attention kernel keeps -m (its running reference maximum) in the same channel of q, so the tensor core
+      // hands it S * scale - m (tc_attn.cu)
+      if (k_one) {
         float* qb = last_packed_bias;
         const float one = 1.0f;
+        const int on = (ch + 15) & ~15;
         for (int h = 0; h < heads; ++h)
-          EO_CHECK_CUDA(cudaMemcpyAsync(qb + (h * 3 + 2) * 64 + 63, &one, sizeof(float), cudaMemcpyHostToDevice, st));
+          EO_CHECK_CUDA(cudaMemcpyAsync(qb + (h * 3 + 1) * 64 + on, &one, sizeof(float), cudaMemcpyHostToDevice, st));
         EO_CHECK_CUDA(cudaStreamSynchronize(st));   // `one` is a stack variable
       }
       if (!fuse) free_act(xn);
@@ -873,11 +892,13 @@ struct eo_unet {
       attn_plans.push_back(nullptr);
       auto prepare = [=]() -> int {
         TcAttnParams ap; ap.qkv = ptr(qkv.off); ap.out = ptr(a.off); ap.B = Bmax; ap.T = T; ap.heads = heads; ap.ch = ch;
-        ap.ones_col = ones_col ? 1 : 0;
+        ap.k_one = k_one ? 1 : 0;
         return tc_attn_plan_create(ap, &attn_plans[ai]);
       };
       push(p + "attention", [=](int B, cudaStream_t stx) -> int { return tc_attn_launch(attn_plans[ai], B, stx); }, 1, prepare);
-      note("k_attn_tc5", 4.0 * heads * (double)T * T * ch, 0, 4.0 * heads * (double)T * T * 64);
+      // executed: S over round16(ch) (+ 16 with the baked maximum) channels, P V over round16(ch) (64 for wide heads)
+      note("k_attn_tc6", 4.0 * heads * (double)T * T * ch, 0,
+           k_one ? 2.0 * heads * (double)T * T * (2 * ((ch + 15) & ~15) + 16) : 4.0 * heads * (double)T * T * 64);
       free_act(qkv);
       rc = plan_conv_tc(p + "proj_out", {seg1x1(a)}, {{wp, C, 1, 0, C}}, C, nullptr, w(p + "proj_out.bias"), nullptr, -1, &x,
                         x.H, x.W, out, st);
@@ -1661,15 +1682,18 @@ int eo_test_attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int
                                     (size_t)ch * 2, (size_t)B * T, cudaMemcpyDeviceToDevice, st));
   TcAttnParams p; p.qkv = padded; p.out = out_bf16; p.B = B; p.T = T; p.heads = heads; p.ch = ch;
   __nv_bfloat16* ones = nullptr;
-  if (ch < 64) {   // channel 63 of every head's v = 1.0 (what the qkv convolution's bias does inside the UNet)
+  if (ch <= 48) {   // channel round16(ch) of every head's k = 1.0 (what the qkv convolution's bias does inside the UNet)
     std::vector<__nv_bfloat16> h1((size_t)B * T, __float2bfloat16(1.0f));
     EO_CHECK_CUDA(cudaMalloc(&ones, h1.size() * sizeof(__nv_bfloat16)));
     EO_CHECK_CUDA(cudaMemcpyAsync(ones, h1.data(), h1.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice, st));
     for (int hh = 0; hh < heads; ++hh)
-      EO_CHECK_CUDA(cudaMemcpy2DAsync(padded + (hh * 3 + 2) * 64 + 63, (size_t)ld * 2, ones, 2, 2, (size_t)B * T,
+      EO_CHECK_CUDA(cudaMemcpy2DAsync(padded + (hh * 3 + 1) * 64 + ((ch + 15) & ~15), (size_t)ld * 2, ones, 2, 2, (size_t)B * T,
                                       cudaMemcpyDeviceToDevice, st));
+    // ... and q multiplied by ch^-1/2 * log2(e), re-rounded to bf16 (inside the UNet the factor sits in the projection's weights)
+    const float sl2 = (1.0f / sqrtf((float)ch)) * 1.4426950408889634f;
+    for (int hh = 0; hh < heads && !rc; ++hh) rc = launch_scale_cols_bf16(padded, (long long)B * T, ld, hh * 3 * 64, ch, sl2, st);
     EO_CHECK_CUDA(cudaStreamSynchronize(st));
-    p.ones_col = 1;
+    p.k_one = 1;
   }
   TcAttnPlan* plan = nullptr;
   rc = tc_attn_plan_create(p, &plan);

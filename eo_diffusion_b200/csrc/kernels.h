@@ -137,18 +137,20 @@ int launch_nhwc_to_nchw_f32(const void* src, int dt, float* dst, int B, int HW, 
 // ---------------------------------------------------------------------------------------
 // Packs torch conv weights w[Cout][Cin_total][k][k] (fp32) into a GEMM operand whose K axis
 // is ordered (source segment, tap, channel).  One call per segment:
-//   dst[n*stride_n + (k_off + tap*C + c)*stride_k] = scale * w[row(n)][cin_off + c][tap]
-// row(n) = row_map ? row_map[n] : n  (row_map[n] < 0 -> zero row); n in [0, Nout).
+//   dst[n*stride_n + (k_off + tap*C + c)*stride_k] = row_scale[n] * w[row(n)][cin_off + c][tap]
+// row(n) = row_map ? row_map[n] : n  (row_map[n] < 0 -> zero row); n in [0, Nout); row_scale (device, optional) = 1.
 // If tap_fold (upsample sub-pixel folding) is non-null it is unused here (see engine).
 int launch_pack_conv_weight(const float* w, int Cin_total, int ksize, int cin_off, int C,
                             void* dst, int dst_dt, long long stride_n, long long stride_k,
-                            int k_off, int Nout, const int* row_map, cudaStream_t st);
+                            int k_off, int Nout, const int* row_map, cudaStream_t st, const float* row_scale = nullptr);
 // wf[Cout][Cin][2][2] = the 3x3 weights w[Cout][Cin][3][3] folded for output parity (a, b) of a nearest x2
 // upsample + conv3x3 (taps at low-resolution rows {a-1, a}, columns {b-1, b})
 int launch_fold_upsample_weight(const float* w, int Cout, int Cin, int a, int b, float* wf, cudaStream_t st);
-// dst[n] = (a ? a[row(n)] : 0) + (b ? b[row(n)] : 0)
+// dst[n] = row_scale[n] * ((a ? a[row(n)] : 0) + (b ? b[row(n)] : 0))
 int launch_pack_bias(const float* a, const float* b, float* dst, int Nout, const int* row_map,
-                     cudaStream_t st);
+                     cudaStream_t st, const float* row_scale = nullptr);
+// x[r][col0 .. col0 + ncols) *= scale, re-rounded to bf16 (rows of ld elements)
+int launch_scale_cols_bf16(void* x, long long rows, int ld, int col0, int ncols, float scale, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------
 // tcgen05 tensor-core kernels (tc_conv.cu / tc_attn.cu)
@@ -210,7 +212,8 @@ struct TcAttnParams {
   const void* qkv = nullptr;  // bf16 [B, T, heads*3*64]: per head q|k|v each padded to 64 channels
   void* out = nullptr;        // bf16 [B, T, heads*ch]
   int B = 0, T = 0, heads = 0, ch = 0;  // ch <= 64
-  int ones_col = 0;           // ch < 64 only: channel 63 of every head's v is 1.0, the kernel takes the softmax row sum from it
+  int k_one = 0;              // ch <= 48 (required there): q arrives multiplied by ch^-1/2 * log2(e) (folded into the qkv
+                              // convolution) and channel round16(ch) of every head's k is 1.0 -- the kernel keeps -m in that channel of q
 };
 struct TcAttnPlan;
 int tc_attn_plan_create(const TcAttnParams& p, TcAttnPlan** out);

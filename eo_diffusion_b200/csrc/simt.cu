@@ -1313,7 +1313,7 @@ namespace {
 __global__ void k_pack_conv_weight(const float* __restrict__ w, int Cin_total, int ksize,
                                    int cin_off, int C, void* __restrict__ dst, int dst_dt,
                                    long long stride_n, long long stride_k, int k_off, int Nout,
-                                   const int* __restrict__ row_map) {
+                                   const int* __restrict__ row_map, const float* __restrict__ row_scale) {
   const int taps = ksize * ksize;
   long long total = (long long)Nout * taps * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -1325,28 +1325,38 @@ __global__ void k_pack_conv_weight(const float* __restrict__ w, int Cin_total, i
     int row = row_map ? row_map[n] : n;
     float v = 0.f;
     if (row >= 0) v = w[((long long)row * Cin_total + cin_off + c) * taps + tap];
+    if (row_scale) v *= row_scale[n];
     long long o = (long long)n * stride_n + (long long)(k_off + tap * C + c) * stride_k;
     if (dst_dt == DT_F32) reinterpret_cast<float*>(dst)[o] = v;
     else reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(v);
   }
 }
 __global__ void k_pack_bias(const float* a, const float* b, float* dst, int Nout,
-                            const int* row_map) {
+                            const int* row_map, const float* row_scale) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= Nout) return;
   int row = row_map ? row_map[n] : n;
   float v = 0.f;
   if (row >= 0) { if (a) v += a[row]; if (b) v += b[row]; }
+  if (row_scale) v *= row_scale[n];
   dst[n] = v;
+}
+// x[r][col0 + c] = bf16(x[r][col0 + c] * scale), c < ncols (the attention self-test's stand-in for a scaled q projection)
+__global__ void k_scale_cols_bf16(__nv_bfloat16* x, long long rows, int ld, int col0, int ncols, float scale) {
+  const long long total = rows * ncols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    __nv_bfloat16* p = x + (i / ncols) * ld + col0 + (int)(i % ncols);
+    *p = __float2bfloat16_rn(__bfloat162float(*p) * scale);
+  }
 }
 }  // namespace
 
 int launch_pack_conv_weight(const float* w, int Cin_total, int ksize, int cin_off, int C,
                             void* dst, int dst_dt, long long stride_n, long long stride_k,
-                            int k_off, int Nout, const int* row_map, cudaStream_t st) {
+                            int k_off, int Nout, const int* row_map, cudaStream_t st, const float* row_scale) {
   long long total = (long long)Nout * ksize * ksize * C;
   k_pack_conv_weight<<<ew_grid(total), 256, 0, st>>>(w, Cin_total, ksize, cin_off, C, dst, dst_dt,
-                                                     stride_n, stride_k, k_off, Nout, row_map);
+                                                     stride_n, stride_k, k_off, Nout, row_map, row_scale);
   EO_CHECK_LAUNCH();
   return EO_OK;
 }
@@ -1382,8 +1392,14 @@ int launch_fold_upsample_weight(const float* w, int Cout, int Cin, int a, int b,
 }
 
 int launch_pack_bias(const float* a, const float* b, float* dst, int Nout, const int* row_map,
-                     cudaStream_t st) {
-  k_pack_bias<<<(unsigned)ceil_div(Nout, 128), 128, 0, st>>>(a, b, dst, Nout, row_map);
+                     cudaStream_t st, const float* row_scale) {
+  k_pack_bias<<<(unsigned)ceil_div(Nout, 128), 128, 0, st>>>(a, b, dst, Nout, row_map, row_scale);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+
+int launch_scale_cols_bf16(void* x, long long rows, int ld, int col0, int ncols, float scale, cudaStream_t st) {
+  k_scale_cols_bf16<<<ew_grid(rows * ncols), 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(x), rows, ld, col0, ncols, scale);
   EO_CHECK_LAUNCH();
   return EO_OK;
 }

@@ -443,7 +443,7 @@ constexpr int OFF6_BAR = OFF5_BAR;
 // q_full, kv_full[S], kv_empty[S], then per tile: s_full, s_free, p_full, pv_done, q_ready
 constexpr int N_BARS6 = 1 + 2 * KV_STAGES5 + 5 * NT5;
 constexpr int ATTN6_SMEM = OFF6_BAR + N_BARS6 * 8 + 16 + 1024;
-constexpr int TM6_S = 0, TM6_P = 32, TM6_O = 48, TM6_Q = 96;
+constexpr int TM6_S = 0, TM6_P = 32, TM6_O = 48, TM6_Q = 96;      // Q: up to 3 + 1 K steps of 8 columns
 
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t v[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -459,6 +459,10 @@ __device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@!p bra WAIT_%=;\n\t}"
       :: "r"(tc::smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(taddr), "r"(v) : "memory");
 }
 
 template <bool TRACE, int ON>      // ON: columns of O = round16(ch); Q in tensor memory below 64
@@ -497,7 +501,10 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
   const int cq = h * 3 * HD, ck = cq + HD, cv = cq + 2 * HD;
   constexpr bool TSQ = ON < HD;
   constexpr int on = ON;
-  constexpr int ksteps = ON / 16;                 // the padded channels of q and k are zero
+  // K steps of S: the channels (the padded ones of q and k are zero) and, with Q in tensor memory, one more whose first
+  // channel is -m in Q (written by the softmax thread of the row) and 1.0 in K (the qkv convolution's bias on that padded
+  // row): the tensor core delivers S * scale - m, the softmax does not spend an FFMA2 per logit pair on it
+  constexpr int ksteps = ON / 16 + (TSQ ? 1 : 0);
 
   if (warp == 4 && lane == 0) {
     tc::tma_prefetch_desc(&map_qkv);
@@ -629,16 +636,21 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
 
       if (TSQ) {
         // this thread's Q row, shared memory (128-byte rows, 16-byte chunk j of row r at position j ^ (r & 7)) ->
-        // tensor memory, 8 packed columns per K step of 16 channels
+        // tensor memory, 8 packed columns per K step of 16 channels (q arrives multiplied by the logit scale, log2
+        // domain: TcAttnParams::k_one); the extra K step starts out zero (reference maximum 0)
         tc::mbar_wait(q_full, 0);
         const uint8_t* qrow = smem + OFF5_Q + t * TILE_BYTES + row * 128;
 #pragma unroll
-        for (int k = 0; k < ksteps; ++k) {
+        for (int k = 0; k < ON / 16; ++k) {
           uint32_t w[8];
           const uint4 c0 = *reinterpret_cast<const uint4*>(qrow + (((2 * k) ^ (row & 7)) << 4));
           const uint4 c1 = *reinterpret_cast<const uint4*>(qrow + (((2 * k + 1) ^ (row & 7)) << 4));
           w[0] = c0.x; w[1] = c0.y; w[2] = c0.z; w[3] = c0.w; w[4] = c1.x; w[5] = c1.y; w[6] = c1.z; w[7] = c1.w;
           tmem_st_32x8(tb + TM6_Q + k * 8, w);
+        }
+        {
+          uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          tmem_st_32x8(tb + TM6_Q + (ON / 16) * 8, z);
         }
         tmem_st_wait();
         tc::tc_fence_before();
@@ -677,14 +689,16 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
 #pragma unroll
         for (int i = 0; i < 32; i += 2)
           mx[(i >> 1) & 3] = max3(mx[(i >> 1) & 3], __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-        return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2;
+        const float mxa = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        return TSQ ? mxa : mxa * scale_log2;      // TSQ: the logits come scaled, relative to the baked maximum
       };
       // pairs k0 .. k1 - 1 of P = 2^(S * scale - m), rounded to bf16 pairs; their sum into l2
       auto exps = [&](const uint32_t (&r)[32], uint32_t (&pk)[16], auto k0c, auto k1c, uint64_t nm2) {
         constexpr int k0 = decltype(k0c)::value, k1 = decltype(k1c)::value;
 #pragma unroll
         for (int k = k0; k < k1; ++k) {
-          const uint64_t x = fma2(pack2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1])), sc2, nm2);
+          const uint64_t v2 = pack2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
+          const uint64_t x = TSQ ? v2 : fma2(v2, sc2, nm2);       // TSQ: S * scale - m straight from the tensor core
           const bool on_fma = POLY_NUM > 0 && ((k * POLY_NUM) % POLY_DEN) < POLY_NUM;
           float p0, p1;
           if (on_fma) {
@@ -699,9 +713,22 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
           pk[k] = *reinterpret_cast<uint32_t*>(&h2);
         }
       };
-      float cm;
+      float cm;                              // SS: scaled row maximum of the next quarter-block
+      float m_pend = 0.f, corr = 0.f;        // TSQ: the raised maximum, and (baked maximum of the row in registers) - m_pend
       bool raise;
-      // Quarter-block q: `v` = its logits, `cm` their scaled row maximum, `raise` the vote (all taken during q - 1).
+      // TSQ: the next quarter-block's logits (in `r`, relative to the baked maximum == m) ask for a higher reference:
+      // choose it (bf16-representable, so the tensor core subtracts it exactly), put it into this row's Q column for
+      // every S issued from now on, and remember the correction of the row already in registers.
+      auto bake = [&](float cmr, float mref) {
+        float f = fmaxf(m, ceilf(cmr + mref));
+        const uint32_t tr = __float_as_uint(f) & 0xffff0000u;          // bf16, rounded towards zero
+        float g = __uint_as_float(tr);
+        if (f > 0.f && g < f) g = __uint_as_float(tr + 0x10000u);       // ... and up (exact for |f| <= 256)
+        m_pend = g;
+        corr = mref - g;
+        tmem_st_32x1(tb + TM6_Q + (ON / 16) * 8, __float_as_uint(-g) >> 16);      // channels (ON, ON + 1) = (-m, 0)
+      };
+      // Quarter-block q: `v` = its logits, `raise` the vote on them (both taken during q - 1).
       // The four softmax warps of a scheduler run in lockstep (same code, same data rates), so nothing but this warp's
       // own arithmetic can cover the latency of a barrier test, tcgen05.ld or tcgen05.st: each is issued early and its
       // result used late.  LAST: no quarter-block q + 1; MASK: quarter-block q + 1 may hold keys beyond T.
@@ -712,10 +739,19 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
         bool pv_seen = q == 0;          // P V_q-1 known complete
         if (raise) {
           // raise the reference maximum: O and l scale by the exact power of two 2^(m_old - m_new)
-          const float m_new = fmaxf(m, ceilf(cm));
+          const float m_new = TSQ ? m_pend : fmaxf(m, ceilf(cm));
           const float alpha = (m_new == m) ? 1.0f : ex2(m - m_new);     // first quarter-block: ex2(-inf) = 0
           m = m_new;
           l2 = fma2(l2, pack2(alpha, alpha), pack2(0.f, 0.f));
+          if (TSQ) {                    // this row was produced against the previous baked maximum
+            const uint64_t c2 = pack2(corr, corr);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float x0, x1;
+              unpack2(add2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2), x0, x1);
+              v[i] = __float_as_uint(x0); v[i + 1] = __float_as_uint(x1);
+            }
+          }
           if (q > 0) {
             bar_spin(B_PVDONE, (q - 1) & 1);
             pv_seen = true;
@@ -752,19 +788,36 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
         if (!pv_seen) tc::tc_fence_after();
         if (TRACE && tlq) tlq[4] = clock64();
         tmem_st_32x16(pa, pk);
-        if (!LAST) {
-          tc::tmem_ld_wait();                       // the row of S_q+1 is in registers: S_q+2 may overwrite it
-          tc::tc_fence_before();
-          bar_arrive(B_SFREE);
-        }
-        if (TRACE && tlq) tlq[5] = clock64();
-        if (!LAST) cm = row_max(vn, MASK ? T - (q + 1) * KQ5 : KQ5);     // covers the latency of the tcgen05.st
-        tmem_st_wait();
-        tc::tc_fence_before();
-        bar_arrive(B_PFULL);                        // the warp's tcgen05.st are complete (wait::st is warp-wide)
-        if (TRACE && tlq) tlq[6] = clock64();
         raise = false;
-        if (!LAST) raise = __any_sync(0xffffffffu, cm > m + RESCALE_THRESHOLD);     // warp-uniform (the TMEM accesses are warp-collective)
+        if (TSQ) {
+          // the maximum / vote on the next row covers the latency of the tcgen05.st; S_q+2 must not be issued before
+          // a raised maximum sits in the Q column, so s_free waits for the vote
+          if (!LAST) {
+            tc::tmem_ld_wait();
+            const float cmr = row_max(vn, MASK ? T - (q + 1) * KQ5 : KQ5);
+            raise = __any_sync(0xffffffffu, cmr > RESCALE_THRESHOLD);       // warp-uniform (the TMEM accesses are warp-collective)
+            if (raise) bake(cmr, m);
+          }
+          if (TRACE && tlq) tlq[5] = clock64();
+          tmem_st_wait();
+          tc::tc_fence_before();
+          if (!LAST) bar_arrive(B_SFREE);
+          bar_arrive(B_PFULL);
+          if (TRACE && tlq) tlq[6] = clock64();
+        } else {
+          if (!LAST) {
+            tc::tmem_ld_wait();                       // the row of S_q+1 is in registers: S_q+2 may overwrite it
+            tc::tc_fence_before();
+            bar_arrive(B_SFREE);
+          }
+          if (TRACE && tlq) tlq[5] = clock64();
+          if (!LAST) cm = row_max(vn, MASK ? T - (q + 1) * KQ5 : KQ5);     // covers the latency of the tcgen05.st
+          tmem_st_wait();
+          tc::tc_fence_before();
+          bar_arrive(B_PFULL);                        // the warp's tcgen05.st are complete (wait::st is warp-wide)
+          if (TRACE && tlq) tlq[6] = clock64();
+          if (!LAST) raise = __any_sync(0xffffffffu, cm > m + RESCALE_THRESHOLD);
+        }
         if (TRACE && tlq) tlq[7] = clock64();
       };
 
@@ -773,10 +826,15 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
       tc::tc_fence_after();
       tc::tmem_ld_32x32(sa, va);
       tc::tmem_ld_wait();
+      raise = true;
+      if (TSQ) {
+        bake(row_max(va, T), 0.f);        // S_0 was issued against a zero Q column
+        tmem_st_wait();
+      } else {
+        cm = row_max(va, T);
+      }
       tc::tc_fence_before();
       bar_arrive(B_SFREE);
-      cm = row_max(va, T);
-      raise = true;
       {
         using F = std::false_type; using Tr = std::true_type;
         int q = 0;
@@ -850,7 +908,7 @@ struct TcAttnPlan {
 int tc_attn_plan_create(const TcAttnParams& p, TcAttnPlan** out) {
   EO_REQUIRE(p.ch <= HD && p.ch % 8 == 0, EO_ERR_ARG,
              "tc_attn: head dimension %d unsupported (must be a multiple of 8, <= 64)", p.ch);
-  EO_REQUIRE(!p.ones_col || p.ch < HD, EO_ERR_ARG, "tc_attn: the row-sum column needs a padded head dimension");
+  EO_REQUIRE((p.k_one != 0) == (p.ch <= 48), EO_ERR_ARG, "tc_attn: heads of <= 48 channels need the 1.0 channel in k (and only they)");
   TcAttnPlan* pl = new TcAttnPlan();
   pl->p = p;
   uint64_t ld = (uint64_t)p.heads * 3 * HD;
@@ -904,7 +962,7 @@ int tc_attn_launch(const TcAttnPlan* pl, int B, cudaStream_t st) {
     const TcAttnParams& p = pl->p;
     float scale_log2 = (1.0f / sqrtf((float)p.ch)) * 1.4426950408889634f;
     dim3 grid((unsigned)ceil_div(p.T, NT5 * QT), (unsigned)p.heads, (unsigned)B);
-    auto kern = p.ones_col ? k_attn_tc5<false, true> : k_attn_tc5<false, false>;
+    auto kern = k_attn_tc5<false, false>;
     EO_CHECK_CUDA(launch_chain(kern, grid, dim3(ATTN5_THREADS), ATTN5_SMEM, st, pl->map, reinterpret_cast<__nv_bfloat16*>(p.out), p.T,
                                p.heads, p.ch, scale_log2, (long long*)nullptr, 0));
     return EO_OK;

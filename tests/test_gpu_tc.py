@@ -57,6 +57,11 @@ def _attn_ref(qkv, heads, ch):
     # QKVAttentionLegacy (unet_openai.py:465-481) on [B, T, heads*3*ch] -> [B, T, heads*ch]
     B, T, _ = qkv.shape
     q, k, v = qkv.float().reshape(B, T, heads, 3, ch).permute(3, 0, 2, 1, 4)   # [B, heads, T, ch]
+    if ch <= 48:
+        # heads of <= 48 channels: the engine folds ch^-1/2 * log2(e) into the q projection, so q reaches the kernel as
+        # bf16(q * that factor); the self-test entry rounds the same way, and so does this reference
+        f = math.log2(math.e) / math.sqrt(ch)
+        q = (q * f).to(torch.bfloat16).float() / f
     s = 1 / math.sqrt(math.sqrt(ch))
     w = torch.softmax(torch.einsum("bhtc,bhsc->bhts", q * s, k * s), dim=-1)
     a = torch.einsum("bhts,bhsc->bhtc", w, v)

@@ -17,6 +17,6 @@ $CMD > $out/plain_${tag}.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_conv_tc3 -s 83 -c 12 -f -o $out/prof_conv3_${tag} \
     $CMD > $out/ncu_conv3_${tag}.log 2>&1
 $CMD > $out/plain_${tag}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_attn_tc5 -s 11 -c 1 -f -o $out/prof_attn_${tag} \
+ncu --set full --clock-control none --import-source on -k regex:k_attn_tc6 -s 11 -c 1 -f -o $out/prof_attn_${tag} \
     $CMD > $out/ncu_attn_${tag}.log 2>&1
 ls -la $out | tail -8
