@@ -2,12 +2,12 @@
 //
 // Replaces QKVAttentionLegacy.forward / QKVAttention.forward (reference
 // backbones/unet_openai.py:465-481, :497-515): softmax_fp32((q*s)^T (k*s)) v with
-// s = ch^-1/4 (applied here once as ch^-1/2 on the fp32 logits), never materialising the
-// [T, T] score matrix in HBM.
+// s = ch^-1/4 (applied once as ch^-1/2: on the fp32 logits for 64-channel heads, folded into the q
+// projection for heads of <= 48 channels), never materialising the [T, T] score matrix in HBM.
 //
 // Layout: qkv is [B, T, heads*3*64] bf16 -- the qkv 1x1 convolution writes each head's q, k
-// and v padded to 64 channels (zero weight rows), so every head dimension <= 64 runs as
-// d = 64 (wider heads take simt.cu's k_attention_wide).  The kernel (k_attn_tc5) is described at its definition.
+// and v padded to 64 channels (zero weight rows); wider heads take simt.cu's k_attention_wide.
+// The kernel (k_attn_tc6) is described at its definition.
 //
 // Roofline: MUFU + issue slots (one ex2 per logit, 4*ch FLOPs per logit); algorithmic FLOPs per launch =
 // 4 * B * heads * T^2 * ch.
@@ -34,23 +34,12 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 2^x on the FMA pipe (k_attn_tc5 takes every third pair of exponentials off the MUFU pipe, its limiter):
-// x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (relative error 7.5e-5,
-// 26 times below the bf16 rounding of P), 2^n added into the exponent field.  x <= 127 - 1; below -125 clamps.
-__device__ __forceinline__ float ex2_fma(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;                   // 1.5 * 2^23: the integer lands in the low mantissa bits
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(0.0551716685295105f, f, 0.2426111251115799f);
-  p = fmaf(p, f, 0.6932609677314758f);
-  p = fmaf(p, f, 0.9999280571937561f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
+// 2^x on the FMA pipe (a share of the exponentials is taken off the MUFU pipe): x = n + f with n = round(x),
+// f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (relative error 7.5e-5, 26 times below the bf16 rounding
+// of P), 2^n added into the exponent field.  x <= 127 - 1; below -125 clamps.  ex2_fma2 below does a pair.
 // Packed fp32 pairs (Blackwell FFMA2 / FADD2: one issue slot for two lanes' worth of a pair): the scale / subtract of
 // every logit pair and the polynomial form of 2^x run on these, halving the issue slots they take next to the MUFU pipe.
 using tc::pack2; using tc::unpack2; using tc::fma2; using tc::add2;
-// ex2_fma of a pair (same arithmetic, element for element)
 __device__ __forceinline__ void ex2_fma2(uint64_t x, float& p0, float& p1) {
   float x0, x1;
   unpack2(x, x0, x1);
@@ -70,17 +59,6 @@ __device__ __forceinline__ void ex2_fma2(uint64_t x, float& p0, float& p1) {
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t v[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
-         "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
-         "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
-         "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
-         "r"(v[31]) : "memory");
-}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -98,52 +76,21 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 #define ATR_T0() const long long _t0 = TRACE ? clock64() : 0
 #define ATR_ACC(var) do { if (TRACE) (var) += clock64() - _t0; } while (0)
 
-// LSUM_MMA: the row sum l comes out of the tensor core -- column 63 of V is 1.0 (head dimension < 64: the
-// qkv convolution's bias on that padded row), so column 63 of O accumulates sum_k P_k in fp32, rescaled
-// with O for free.  Otherwise the softmax threads add the rounded P values up themselves.
-
-// =====================================================================================================
-// k_attn_tc5: FOUR query tiles per CTA, 32-key quarter-blocks.
-//
-// A first kernel with TWO query tiles per CTA and 64-key half-blocks kept the MUFU pipe 61 % busy
-// (profiles/r01c_attn_tc_v4_ncu.txt: xu 61 %, tensor 30 %; trace: 1740 clk per 64-key half-block of which the exp
-// pass is 1150 and 400 are waits): with one warp of each tile per scheduler, the fixed latencies of every hand-off (a satisfied mbarrier.try_wait alone costs
-// ~100 clk, tcgen05.ld, the maximum tree, the vote, tcgen05.st + wait) leave the other warp alone on the pipe.
-// Here each scheduler holds FOUR softmax warps (one per tile):
-//   * tensor memory per tile: two 32-column S buffers (fp32 logits of one 32-key quarter-block) + 64 columns
-//     O; P (packed bf16 pairs, 16 columns) is written over the first half of the S buffer it came from once
-//     the row has been read -- 4 x 128 = 512 columns;
-//   * S_q+1 was issued a whole exp pass before the softmax of quarter-block q ends (into the other buffer);
-//     S_q+2 is issued right behind P V_q, whose P it overwrites -- tcgen05.mma of one thread execute in order;
-//   * the reference maximum m is kept INTEGER (log2 domain), so raising it rescales O and l by an exact power
-//     of two.
-// Measured, clk per 64 keys and tile (tools/attn_trace.py, B200): two tiles 869; this kernel 701.  Variants
-// that lost: 64-key S aliased with P in ONE buffer per tile 731 (258 of them the serial P V -> S chain); three
-// tiles with Q in tensor memory (S as a TS MMA, 16 instead of 40 clk per step: an MMA with A in shared memory
-// costs (128 + N) * 32 B / 128 B/clk, tools/probe_mma_dep.cu) 763 -- the tensor pipe is not the limiter, the
-// fourth warp per scheduler is worth more; the same with separate P buffers and S released at tcgen05.ld 918,
-// and with the next row's tcgen05.ld software-pipelined into the exp pass 1090.
-// Warps (768 threads, registers redistributed with setmaxnreg): 0..3 MMA issuers of tile 0..3, 4 TMA loader
-// (5..7 idle), 8..23 softmax (tile (w-8)/4, TMEM lane quadrant w % 4).
-// =====================================================================================================
-constexpr int NT5 = 4;
-constexpr int KQ5 = 32;                      // keys per quarter-block
-constexpr int KV_STAGES5 = 4;
-constexpr int OFF5_Q = 0;
-constexpr int OFF5_K = OFF5_Q + NT5 * TILE_BYTES;
-constexpr int OFF5_V = OFF5_K + KV_STAGES5 * TILE_BYTES;
-constexpr int OFF5_BAR = OFF5_V + KV_STAGES5 * TILE_BYTES;
-// q_full, kv_full[S], kv_empty[S], s_full[4][2], p_full[4][2], pv_late[4], o_done[4]
-constexpr int N_BARS5 = 1 + 2 * KV_STAGES5 + 6 * NT5;
-constexpr int ATTN5_SMEM = OFF5_BAR + N_BARS5 * 8 + 16 + 1024;
-constexpr int ATTN5_THREADS = 768;
+constexpr int NTILE = 4;
+constexpr int KQ = 32;                      // keys per quarter-block
+constexpr int KV_STAGES = 4;
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + NTILE * TILE_BYTES;
+constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
+constexpr int OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
+constexpr int ATTN_THREADS = 768;
 constexpr int SM_WARP0 = 8;
 // POLY_NUM of every POLY_DEN pairs of exponentials run on the FMA pipe (0 = none)
 #ifndef EO_ATTN_POLY_NUM
 #define EO_ATTN_POLY_NUM 1
 #endif
 #ifndef EO_ATTN_POLY_DEN
-#define EO_ATTN_POLY_DEN 3
+#define EO_ATTN_POLY_DEN 4
 #endif
 constexpr int POLY_NUM = EO_ATTN_POLY_NUM, POLY_DEN = EO_ATTN_POLY_DEN;
 
@@ -163,286 +110,48 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t v[1
          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 
-// trace slots (TRACE instantiation): 0 lifetime; softmax warp of tile 0, quadrant 0: 1 waits on S, 2 tcgen05.ld
-// of the row, 3 maximum + vote (+ raise), 4 exponentials + packing, 5 tcgen05.st + hand-over; 6 issuer 0 waits
-// on P; 7 HALF-blocks (64 keys, comparable with k_attn_tc's slot)
-template <bool TRACE, bool LSUM_MMA>
-__global__ void __launch_bounds__(ATTN5_THREADS, 1)
-k_attn_tc5(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out, int T,
-           int heads, int ch, float scale_log2, long long* trace, int trace_n) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF5_BAR);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + KV_STAGES5;
-  uint64_t* s_full = kv_empty + KV_STAGES5;   // [tile][buffer]: S_q is complete
-  uint64_t* p_full = s_full + 2 * NT5;        // [tile][buffer], 128 arrivals: P_q is in tensor memory
-  uint64_t* pv_late = p_full + 2 * NT5;       // [tile]: the second-to-last P V has completed
-  uint64_t* o_done = pv_late + NT5;           // [tile]: the last P V has completed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + NT5);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long t_entry = TRACE ? clock64() : 0;
-  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  long long* trc = (TRACE && cta_lin < trace_n) ? trace + (long long)cta_lin * 8 : nullptr;
-  const int q0 = blockIdx.x * NT5 * QT, h = blockIdx.y, b = blockIdx.z;
-  const int ntiles = min(NT5, (T - q0 + QT - 1) / QT);
-  const int nblk = (T + KT - 1) / KT;
-  const int nq = (T + KQ5 - 1) / KQ5;          // quarter-blocks that hold at least one key
-  const int cq = h * 3 * HD, ck = cq + HD, cv = cq + 2 * HD;
-
-  if (warp == 4 && lane == 0) {
-    tc::tma_prefetch_desc(&map_qkv);
-    tc::mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES5; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], ntiles); }
-    for (int i = 0; i < 2 * NT5; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 128); }
-    for (int i = 0; i < NT5; ++i) { tc::mbar_init(&pv_late[i], 1); tc::mbar_init(&o_done[i], 1); }
-    tc::fence_barrier_init();
-  }
-  if (warp == 0) { tc::tmem_alloc(tmem_ptr, TM_COLS); tc::tmem_relinquish(); }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  pdl_wait();            // the qkv convolution may still have been running while this CTA set itself up (common.cuh)
-  pdl_trigger();
-
-  // 768 threads leave 80 registers each: the issue warpgroup drops to 40, the loader's to 24, the four softmax
-  // warpgroups grow to 104 (40 + 24 + 4 * 104 = 480 = 6 * 80)
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    // ---------------------------------------------------------------- MMA issuer of tile `warp`
-    if (warp < ntiles) {
-      const int t = warp;
-      constexpr uint32_t idesc_s = tc::make_idesc_bf16(128, KQ5, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = tc::make_idesc_bf16(128, HD, 0, 1);   // P (TMEM) x V (MN-major)
-      constexpr uint32_t TILE16 = TILE_BYTES >> 4, QUART16 = (KQ5 * 128) >> 4;
-      const uint64_t qdesc = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_Q)) + (uint64_t)(t * TILE16);
-      const uint64_t kdesc0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_K));
-      const uint64_t vdesc0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_V));
-      const uint32_t d_s = tmem + t * 128, d_o = d_s + 64;
-      const int ksteps = (ch + 15) >> 4;        // the padded channels of q and k are zero
-      // S_q = Q_t K_q^T into S buffer q & 1; quarter-block q = rows 32*(q & 3).. of the K tile in `stage`
-      auto issue_s = [&](int q, uint32_t stage) {
-        if (tc::elect_one()) {
-          const uint64_t kdesc = kdesc0 + (uint64_t)(stage * TILE16 + (q & 3) * QUART16);
-          const uint32_t d = d_s + (q & 1) * KQ5;
-          for (int k = 0; k < ksteps; ++k)
-            tc::umma_f16_ss(d, tc::desc_advance(qdesc, k * 32), tc::desc_advance(kdesc, k * 32), idesc_s, k != 0 ? 1u : 0u);
-          tc::umma_commit(&s_full[t * 2 + (q & 1)]);
-        }
-        __syncwarp();
-      };
-      // O_t (+)= P_q V_q; P_q = packed bf16 pairs in the first 16 columns of S buffer q & 1
-      auto issue_pv = [&](int q, uint32_t stage, bool release_kv, bool last) {
-        if (tc::elect_one()) {
-          const uint64_t vdesc = vdesc0 + (uint64_t)(stage * TILE16 + (q & 3) * QUART16);
-          const uint32_t pa = d_s + (q & 1) * KQ5;
-#pragma unroll
-          for (int k = 0; k < KQ5 / 16; ++k)     // A: 16 keys = 8 packed columns of P; B: 16 rows of 128 B of V
-            umma_f16_ts(d_o, pa + k * 8, tc::desc_advance(vdesc, k * 16 * 128), idesc_o, (q != 0 || k != 0) ? 1u : 0u);
-          if (q == nq - 2) tc::umma_commit(&pv_late[t]);      // only the last quarter-block's raise path needs it
-          if (release_kv) tc::umma_commit(&kv_empty[stage]);
-          if (last) tc::umma_commit(&o_done[t]);
-        }
-        __syncwarp();
-      };
-      long long tr_p = 0;
-      tc::mbar_wait(q_full, 0);
-      tc::mbar_wait(&kv_full[0], 0);
-      tc::tc_fence_after();
-      issue_s(0, 0);
-      if (nq > 1) issue_s(1, 0);
-      uint32_t st = 0;                  // stage of the K/V tile of quarter-block q
-      uint32_t st2 = 0, ph2 = 0;        // stage / phase of the K/V tile of quarter-block q + 2
-      for (int q = 0; q < nq; ++q) {
-        const bool last = q == nq - 1;
-        // the K/V tile of quarter-block q + 2 (a new one when q + 2 is a multiple of 4)
-        if (q + 2 < nq && ((q + 2) & 3) == 0) {
-          if (++st2 == KV_STAGES5) { st2 = 0; ph2 ^= 1; }
-          tc::mbar_wait(&kv_full[st2], ph2);
-        }
-        { ATR_T0(); tc::mbar_wait(&p_full[t * 2 + (q & 1)], (q >> 1) & 1); ATR_ACC(tr_p); }
-        tc::tc_fence_after();
-        issue_pv(q, st, (q & 3) == 3 || last, last);
-        if (q + 2 < nq) issue_s(q + 2, st2);      // in order behind P V_q, whose P it overwrites
-        if ((q & 3) == 3) { if (++st == KV_STAGES5) st = 0; }
-      }
-      if (trc && warp == 0 && lane == 0) { trc[6] = tr_p; trc[7] = (nq + 1) / 2; }
-    }
-  } else if (warp < SM_WARP0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-    // ---------------------------------------------------------------- TMA loader (warp 4)
-    if (warp == 4) {
-      if (tc::elect_one()) {
-        tc::mbar_arrive_expect_tx(q_full, ntiles * TILE_BYTES);
-        for (int t = 0; t < ntiles; ++t)
-          tc::tma_load_3d(smem + OFF5_Q + t * TILE_BYTES, &map_qkv, q_full, cq, q0 + t * QT, b);
-      }
-      __syncwarp();
-      uint32_t s = 0, ph = 0;
-      for (int j = 0; j < nblk; ++j) {
-        tc::mbar_wait(&kv_empty[s], ph ^ 1);
-        if (tc::elect_one()) {
-          tc::mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-          tc::tma_load_3d(smem + OFF5_K + s * TILE_BYTES, &map_qkv, &kv_full[s], ck, j * KT, b);
-          tc::tma_load_3d(smem + OFF5_V + s * TILE_BYTES, &map_qkv, &kv_full[s], cv, j * KT, b);
-        }
-        __syncwarp();
-        if (++s == KV_STAGES5) { s = 0; ph ^= 1; }
-      }
-    }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    // ---------------------------------------------------------------- softmax / output: thread <-> query row
-    const int t = (warp - SM_WARP0) >> 2;
-    if (t < ntiles) {
-      const int qd = warp & 3;
-      const int row = qd * 32 + lane;
-      const uint32_t sp = tmem + ((uint32_t)(qd * 32) << 16) + t * 128;   // the two S buffers (P over their first halves)
-      const uint32_t oa = sp + 64;
-      float m = -INFINITY, l = 0.f;          // m: integer-valued reference maximum (log2 domain)
-      long long tr_s = 0, tr_exp = 0, tr_ld = 0, tr_max = 0, tr_st = 0;
-
-      for (int q = 0; q < nq; ++q) {
-        const int buf = q & 1;
-        const uint32_t sb = sp + buf * KQ5;
-        { ATR_T0(); tc::mbar_wait(&s_full[t * 2 + buf], (q >> 1) & 1); ATR_ACC(tr_s); }
-        tc::tc_fence_after();
-        const int nvalid = T - q * KQ5;        // < KQ5 only in a ragged last quarter-block
-        uint32_t v[32], pk[16];
-        long long tq0 = TRACE ? clock64() : 0;
-        tc::tmem_ld_32x32(sb, v);
-        tc::tmem_ld_wait();
-        if (TRACE) { const long long c = clock64(); tr_ld += c - tq0; tq0 = c; }
-        if (nvalid < KQ5) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i >= nvalid) v[i] = 0xff800000u;   // -inf
-        }
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          mx[(i >> 1) & 3] = max3(mx[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-        const float cm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2;
-        // warp-uniform decision (the TMEM accesses are warp-collective)
-        if (__any_sync(0xffffffffu, cm > m + RESCALE_THRESHOLD)) {
-          // raise the reference maximum: O and l scale by the exact power of two 2^(m_old - m_new)
-          const float m_new = fmaxf(m, ceilf(cm));
-          const float alpha = (m_new == m) ? 1.0f : ex2(m - m_new);     // first quarter-block: ex2(-inf) = 0
-          m = m_new;
-          l *= alpha;
-          if (q > 0) {
-            // P V_q-1 must have landed (s_full(q) only covers P V_q-2): S_q+1 was issued behind it, so its
-            // barrier says so too; the last quarter-block has a commit of its own
-            if (q + 1 < nq) tc::mbar_wait(&s_full[t * 2 + (buf ^ 1)], ((q + 1) >> 1) & 1);
-            else tc::mbar_wait(&pv_late[t], 0);
-            tc::tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < HD; c += 16) {
-              uint32_t o[16];
-              tmem_ld_32x16(oa + c, o);
-              tc::tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x16(oa + c, o);
-            }
-          }
-        }
-        if (TRACE) { const long long c = clock64(); tr_max += c - tq0; tq0 = c; }
-        float rs0 = 0.f, rs1 = 0.f;
-        const uint64_t sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m, -m);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const uint64_t x = fma2(pack2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), sc2, nm2);
-          const bool on_fma = POLY_NUM > 0 && ((k * POLY_NUM) % POLY_DEN) < POLY_NUM;
-          float p0, p1;
-          if (on_fma) {
-            ex2_fma2(x, p0, p1);
-          } else {
-            float x0, x1;
-            unpack2(x, x0, x1);
-            p0 = ex2(x0); p1 = ex2(x1);
-          }
-          if (!LSUM_MMA) { rs0 += p0; rs1 += p1; }
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-          pk[k] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-        if (TRACE) { const long long c = clock64(); tr_exp += c - tq0; tq0 = c; }
-        tmem_st_32x16(sb, pk);          // the row of S has been read: P goes over its first half
-        l += rs0 + rs1;
-        tmem_st_wait();
-        tc::tc_fence_before();
-        tc::mbar_arrive(&p_full[t * 2 + buf]);
-        if (TRACE) { const long long c = clock64(); tr_st += c - tq0; }
-      }
-      if (trc && warp == SM_WARP0 && lane == 0) { trc[1] = tr_s; trc[2] = tr_ld; trc[3] = tr_max; trc[4] = tr_exp; trc[5] = tr_st; }
-      tc::mbar_wait(&o_done[t], 0);
-      tc::tc_fence_after();
-      const int qi = q0 + t * QT + row;
-      __nv_bfloat16* op = out + ((long long)b * T + qi) * (heads * ch) + h * ch;
-      float inv = 1.0f / l;
-#pragma unroll
-      for (int c = HD - 32; c >= 0; c -= 32) {      // upper half first: it holds the row sum
-        uint32_t o[32];
-        tc::tmem_ld_32x32(oa + c, o);
-        tc::tmem_ld_wait();
-        if (LSUM_MMA && c == HD - 32) inv = 1.0f / __uint_as_float(o[31]);
-        if (qi < T) {
-#pragma unroll
-          for (int d = 0; d < 32; d += 8) {
-            if (c + d < ch) {
-              uint4 w4;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w4);
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                h2[e] = __floats2bfloat162_rn(__uint_as_float(o[d + 2 * e]) * inv,
-                                              __uint_as_float(o[d + 2 * e + 1]) * inv);
-              *reinterpret_cast<uint4*>(op + c + d) = w4;
-            }
-          }
-        }
-      }
-      tc::tc_fence_before();
-    }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    __syncwarp();
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem, TM_COLS);
-  }
-  if (trc && threadIdx.x == 0) trc[0] = clock64() - t_entry;
-}
-
-
 // =====================================================================================================
-// k_attn_tc6: k_attn_tc5's four tiles and 32-key quarter-blocks with the hand-offs taken off the critical path.
+// k_attn_tc6: FOUR 128-query tiles per CTA, keys consumed in 32-key quarter-blocks (rounds).
 //
-// A clock64 timeline of k_attn_tc5 (tools/attn_timeline.py) showed its four tiles running in LOCKSTEP: every softmax
-// warp of a scheduler sat in the same phase at the same time (all four queueing for the MUFU pipe, then all four in the
-// barrier wait / tcgen05.ld / maximum / vote with the MUFU pipe idle), and then all four issuers pushed their five MMAs
-// into the one tensor pipe at once (736 clk per round, the S MMA at N = 32 costs 40 clk for 16 clk of work because it
-// re-reads Q from shared memory) while every softmax warp waited for S.  Here
-//   * the softmax is software-pipelined across quarter-blocks: the row of S_q+1 is fetched into a second register set
-//     behind the first half of the exponentials of S_q (tcgen05.ld is asynchronous until its registers are read), its
-//     maximum and the raise vote are taken after P_q has been handed over -- a warp's instruction stream has MUFU work
-//     nearly all the time and never waits on a barrier that has not long completed;
-//   * S has ONE 32-column buffer per tile, released when its row is in registers (s_free) instead of when P has been
-//     consumed, and P a buffer of its own: S_q+2 is issued half a round earlier than before;
+// 768 threads (registers redistributed with setmaxnreg): warps 0..3 MMA issuers of tile 0..3 (one thread each), 4 TMA
+// loader (K/V tiles of 128 keys, 4 stages; 5..7 idle), 8..23 softmax (tile (w-8)/4, TMEM lane quadrant w % 4, thread <->
+// query row): every warp scheduler holds one softmax warp of each tile.  Per round and tile: S_q = Q K_q^T (M128 N32)
+// into the tile's S columns; the softmax thread of a row takes P = exp2(S * scale - m) against an INTEGER-valued lazily
+// raised reference maximum m (O and l rescaled in place by an exact power of two, only when a logit exceeds m by 2^8)
+// and writes P as packed bf16 pairs into the tile's P columns; O += P V_q is a TS MMA (A = P from tensor memory, V
+// MN-major straight from its TMA tile).  A share of the exponentials runs on the FMA pipe (ex2_fma2, packed fp32x2).
+//
+// What shaped it (round 2; tools/attn_timeline.py = a clock64 timeline of the softmax warps of one scheduler and of
+// the issuers): the predecessor handed S and P back and forth through one aliased buffer pair and ran its four tiles
+// in LOCKSTEP -- every softmax warp of a scheduler in the same phase at the same time (all four queueing for the MUFU
+// pipe, then all four in barrier wait / tcgen05.ld / maximum / vote with the MUFU pipe idle), while the issuer warps,
+// which get every fifth issue slot of their scheduler at best, needed 500-700 clk to get five MMAs out.  Hence:
+//   * the softmax is software-pipelined across rounds: the row of S_q+1 is fetched into a second register set behind
+//     the first exponentials of S_q (tcgen05.ld is asynchronous until its registers are read), barrier tests are
+//     issued early and consumed late, the maximum / vote on S_q+1 covers the latency of the tcgen05.st of P_q -- a
+//     warp's own arithmetic hides its latencies, lockstep or not;
+//   * S has ONE 32-column buffer per tile, released when its row is in registers (s_free), and P a buffer of its
+//     own; the issuer puts S_q+2 ahead of P V_q (S is what the softmax needs next, P V_q only has to land before
+//     P_q+1 is written);
+//   * the issuer is ONE thread running an unrolled loop: ~45 instructions per round instead of ~110;
 //   * TSQ (head dimension <= 48, the T = 4096 blocks): the softmax threads copy their Q row into tensor memory once, so
-//     S = Q K^T is a TS MMA (16 clk per K step instead of 40) and O is only round16(ch) columns wide: tensor time per
-//     round and tile 48 + 48 instead of 120 + 64 clk.  Wider heads keep Q in shared memory and a 64-column O.
-// Tensor memory per tile (128 columns): S 0..31, P 32..47 (packed bf16 pairs), O 48..48+ON, Q 96..96+ON/2 (TSQ).
-// Barriers per tile: s_full (commit of S_q), s_free (128 threads: row read), p_full (128 threads: P_q written), pv_done (commit
-// of P V_q; the softmax waits for P V_q-1 before it overwrites P or rescales O), q_ready (4 warps: Q copied).
-// The row sum l is accumulated by the softmax threads (packed fp32 adds).
+//     S = Q K^T is a TS MMA (16 clk per K step instead of 40: an SS MMA at N = 32 re-reads Q from shared memory), O
+//     is only round16(ch) columns wide, and one extra K step carries (-m) x 1.0: q arrives multiplied by the logit
+//     scale (folded into the qkv projection, TcAttnParams::k_one), the thread keeps -m in a spare channel of its Q
+//     row, k has 1.0 there -- the tensor core delivers S * scale - m and the softmax spends no FFMA2 per logit pair
+//     on it.  A raised maximum is written to the Q column BEFORE s_free lets the next S be issued; the one row
+//     already in registers gets the difference added (corr).  64-channel heads keep Q in shared memory, a 64-column
+//     O and the FFMA2.
+// Tensor memory per tile (128 columns): S 0..31, P 32..47 (packed bf16 pairs), O 48..48+ON, Q 96..96+ON/2+8 (TSQ).
+// Barriers per tile: s_full (commit of S_q), s_free (128 threads: row read), p_full (128 threads: P_q written),
+// pv_done (commit of P V_q; the softmax waits for P V_q-1 before it overwrites P or rescales O), q_ready (4 warps: Q
+// copied).  The row sum l is accumulated by the softmax threads (packed fp32 adds).
+// Measured (B200, 64 x 8 heads, T = 4096, ch = 48, kernel alone at ~1.9 GHz): predecessor 2.42 ms; pipelined softmax +
+// lean issuer 2.28; + baked scale / maximum 2.12 (778 TFLOP/s algorithmic).  ncu: MUFU pipe 71 %, issue slots 62 %.
 // =====================================================================================================
-constexpr int OFF6_BAR = OFF5_BAR;
 // q_full, kv_full[S], kv_empty[S], then per tile: s_full, s_free, p_full, pv_done, q_ready
-constexpr int N_BARS6 = 1 + 2 * KV_STAGES5 + 5 * NT5;
-constexpr int ATTN6_SMEM = OFF6_BAR + N_BARS6 * 8 + 16 + 1024;
+constexpr int N_BARS = 1 + 2 * KV_STAGES + 5 * NTILE;
+constexpr int ATTN_SMEM = OFF_BAR + N_BARS * 8 + 16 + 1024;
 constexpr int TM6_S = 0, TM6_P = 32, TM6_O = 48, TM6_Q = 96;      // Q: up to 3 + 1 K steps of 8 columns
 
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t v[8]) {
@@ -466,21 +175,21 @@ __device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
 }
 
 template <bool TRACE, int ON>      // ON: columns of O = round16(ch); Q in tensor memory below 64
-__global__ void __launch_bounds__(ATTN5_THREADS, 1)
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
 k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out, int T,
            int heads, int ch, float scale_log2, long long* trace, int trace_n) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF6_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + KV_STAGES5;
-  uint64_t* s_full = kv_empty + KV_STAGES5;   // [tile]
-  uint64_t* s_free = s_full + NT5;
-  uint64_t* p_full = s_free + NT5;
-  uint64_t* pv_done = p_full + NT5;
-  uint64_t* q_ready = pv_done + NT5;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_ready + NT5);
+  uint64_t* kv_empty = kv_full + KV_STAGES;
+  uint64_t* s_full = kv_empty + KV_STAGES;   // [tile]
+  uint64_t* s_free = s_full + NTILE;
+  uint64_t* p_full = s_free + NTILE;
+  uint64_t* pv_done = p_full + NTILE;
+  uint64_t* q_ready = pv_done + NTILE;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_ready + NTILE);
 
   // warp index through a shuffle: the compiler then knows it (and the tile, quadrant, barrier and tensor-memory
   // addresses derived from it) to be warp-uniform and keeps them in uniform registers
@@ -494,10 +203,10 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
   // [tile][round][4] = round starts, next S issued, saw P, P V issued
   constexpr int TL_CTA = 150, TL_Q0 = 48, TL_N = 16;
   long long* tl = (TRACE && cta_lin == TL_CTA && trace_n > TL_CTA) ? trace + (long long)trace_n * 8 : nullptr;
-  const int q0 = blockIdx.x * NT5 * QT, h = blockIdx.y, b = blockIdx.z;
-  const int ntiles = min(NT5, (T - q0 + QT - 1) / QT);
+  const int q0 = blockIdx.x * NTILE * QT, h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = min(NTILE, (T - q0 + QT - 1) / QT);
   const int nblk = (T + KT - 1) / KT;
-  const int nq = (T + KQ5 - 1) / KQ5;          // quarter-blocks that hold at least one key
+  const int nq = (T + KQ - 1) / KQ;          // quarter-blocks that hold at least one key
   const int cq = h * 3 * HD, ck = cq + HD, cv = cq + 2 * HD;
   constexpr bool TSQ = ON < HD;
   constexpr int on = ON;
@@ -509,8 +218,8 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
   if (warp == 4 && lane == 0) {
     tc::tma_prefetch_desc(&map_qkv);
     tc::mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES5; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], ntiles); }
-    for (int i = 0; i < NT5; ++i) {
+    for (int s = 0; s < KV_STAGES; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], ntiles); }
+    for (int i = 0; i < NTILE; ++i) {
       tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_free[i], 128); tc::mbar_init(&p_full[i], 128);
       tc::mbar_init(&pv_done[i], 1); tc::mbar_init(&q_ready[i], 4);
     }
@@ -530,17 +239,16 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // ---------------------------------------------------------------- MMA issuer of tile `warp`: ONE thread runs the
     // whole loop.  The issuer shares its scheduler with four busy softmax warps and gets every fifth issue slot at
-    // best, so what bounds a round is how many instructions the issuer needs per quarter-block (tools/attn_timeline.py:
-    // the rolled loop of k_attn_tc5 took 500-700 clk to get five MMAs out).  Unrolled over the four K/V stages and the
-    // four quarter-blocks of a tile every descriptor is a constant offset from one base and every parity a constant.
+    // best, so every instruction in its loop counts: unrolled over the four quarter-blocks of a K/V tile, every
+    // descriptor is a constant offset from one base and every parity a constant.
     if (warp < ntiles && tc::elect_one()) {
       const int t = warp;
-      constexpr uint32_t idesc_s = tc::make_idesc_bf16(128, KQ5, 0, 0);  // Q (K-major / tensor memory) x K (K-major)
+      constexpr uint32_t idesc_s = tc::make_idesc_bf16(128, KQ, 0, 0);  // Q (K-major / tensor memory) x K (K-major)
       constexpr uint32_t idesc_o = tc::make_idesc_bf16(128, on, 0, 1);   // P (tensor memory) x V (MN-major)
-      constexpr uint32_t TILE16 = TILE_BYTES >> 4, QUART16 = (KQ5 * 128) >> 4;
-      const uint64_t qdesc = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_Q)) + (uint64_t)(t * TILE16);
-      const uint64_t kd0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_K));
-      const uint64_t vd0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF5_V));
+      constexpr uint32_t TILE16 = TILE_BYTES >> 4, QUART16 = (KQ * 128) >> 4;
+      const uint64_t qdesc = tc::make_sw128_desc(tc::smem_u32(smem + OFF_Q)) + (uint64_t)(t * TILE16);
+      const uint64_t kd0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF_K));
+      const uint64_t vd0 = tc::make_sw128_desc(tc::smem_u32(smem + OFF_V));
       const uint32_t tb = tmem + t * 128;
       // S = Q_t K^T for the quarter-block whose K rows start at descriptor `kd`
       auto issue_s = [&](uint64_t kd) {
@@ -567,8 +275,8 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
       uint64_t kd = kd0, vd = vd0;      // descriptors of K/V tile `blk`
       for (int blk = 0; blk < nblk; ++blk) {
         // stage / phase / descriptors of K/V tile blk + 1
-        const uint32_t st1 = (st + 1 == KV_STAGES5) ? 0u : st + 1;
-        const uint32_t ph1 = (st + 1 == KV_STAGES5) ? (kvph ^ 1) : kvph;
+        const uint32_t st1 = (st + 1 == KV_STAGES) ? 0u : st + 1;
+        const uint32_t ph1 = (st + 1 == KV_STAGES) ? (kvph ^ 1) : kvph;
         const uint64_t kd1 = kd0 + (uint64_t)(st1 * TILE16);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -605,7 +313,7 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
       if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(q_full, ntiles * TILE_BYTES);
         for (int t = 0; t < ntiles; ++t)
-          tc::tma_load_3d(smem + OFF5_Q + t * TILE_BYTES, &map_qkv, q_full, cq, q0 + t * QT, b);
+          tc::tma_load_3d(smem + OFF_Q + t * TILE_BYTES, &map_qkv, q_full, cq, q0 + t * QT, b);
       }
       __syncwarp();
       uint32_t s = 0, ph = 0;
@@ -613,11 +321,11 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
         tc::mbar_wait(&kv_empty[s], ph ^ 1);
         if (tc::elect_one()) {
           tc::mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-          tc::tma_load_3d(smem + OFF5_K + s * TILE_BYTES, &map_qkv, &kv_full[s], ck, j * KT, b);
-          tc::tma_load_3d(smem + OFF5_V + s * TILE_BYTES, &map_qkv, &kv_full[s], cv, j * KT, b);
+          tc::tma_load_3d(smem + OFF_K + s * TILE_BYTES, &map_qkv, &kv_full[s], ck, j * KT, b);
+          tc::tma_load_3d(smem + OFF_V + s * TILE_BYTES, &map_qkv, &kv_full[s], cv, j * KT, b);
         }
         __syncwarp();
-        if (++s == KV_STAGES5) { s = 0; ph ^= 1; }
+        if (++s == KV_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -639,7 +347,7 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
         // tensor memory, 8 packed columns per K step of 16 channels (q arrives multiplied by the logit scale, log2
         // domain: TcAttnParams::k_one); the extra K step starts out zero (reference maximum 0)
         tc::mbar_wait(q_full, 0);
-        const uint8_t* qrow = smem + OFF5_Q + t * TILE_BYTES + row * 128;
+        const uint8_t* qrow = smem + OFF_Q + t * TILE_BYTES + row * 128;
 #pragma unroll
         for (int k = 0; k < ON / 16; ++k) {
           uint32_t w[8];
@@ -661,7 +369,7 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
       // pv_done + 96 bytes): the compiler would otherwise re-derive every address from the warp index at every use
       uint32_t bar_t = tc::smem_u32(&s_full[t]);
       asm volatile("mov.u32 %0, %0;" : "+r"(bar_t));
-      constexpr int B_SFULL = 0, B_SFREE = NT5 * 8, B_PFULL = 2 * NT5 * 8, B_PVDONE = 3 * NT5 * 8;
+      constexpr int B_SFULL = 0, B_SFREE = NTILE * 8, B_PFULL = 2 * NTILE * 8, B_PVDONE = 3 * NTILE * 8;
       // one non-blocking test (its latency overlaps the arithmetic that follows), then a spin only if it failed
       auto bar_test = [&](int off, uint32_t parity) -> uint32_t {
         uint32_t ok;
@@ -680,7 +388,7 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
 
       // scaled row maximum of a quarter-block (MASK: keys beyond T set to -inf in the registers)
       auto row_max = [&](uint32_t (&r)[32], int nvalid) -> float {
-        if (nvalid < KQ5) {
+        if (nvalid < KQ) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (i >= nvalid) r[i] = 0xff800000u;   // -inf
@@ -794,7 +502,7 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
           // a raised maximum sits in the Q column, so s_free waits for the vote
           if (!LAST) {
             tc::tmem_ld_wait();
-            const float cmr = row_max(vn, MASK ? T - (q + 1) * KQ5 : KQ5);
+            const float cmr = row_max(vn, MASK ? T - (q + 1) * KQ : KQ);
             raise = __any_sync(0xffffffffu, cmr > RESCALE_THRESHOLD);       // warp-uniform (the TMEM accesses are warp-collective)
             if (raise) bake(cmr, m);
           }
@@ -811,7 +519,7 @@ k_attn_tc6(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restric
             bar_arrive(B_SFREE);
           }
           if (TRACE && tlq) tlq[5] = clock64();
-          if (!LAST) cm = row_max(vn, MASK ? T - (q + 1) * KQ5 : KQ5);     // covers the latency of the tcgen05.st
+          if (!LAST) cm = row_max(vn, MASK ? T - (q + 1) * KQ : KQ);     // covers the latency of the tcgen05.st
           tmem_st_wait();
           tc::tc_fence_before();
           bar_arrive(B_PFULL);                        // the warp's tcgen05.st are complete (wait::st is warp-wide)
@@ -929,17 +637,17 @@ static int attn6_launch(const TcAttnPlan* pl, int B, cudaStream_t st, long long*
   // logits = (q . k) * ch^-1/2 ; softmax evaluated with exp2
   float scale_log2 = (1.0f / sqrtf((float)p.ch)) * 1.4426950408889634f;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-  dim3 grid((unsigned)ceil_div(p.T, NT5 * QT), (unsigned)p.heads, (unsigned)B);
+  dim3 grid((unsigned)ceil_div(p.T, NTILE * QT), (unsigned)p.heads, (unsigned)B);
   static bool attr_set = false;        // per instantiation (TRACE)
   if (!attr_set) {
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN6_SMEM));
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN6_SMEM));
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN6_SMEM));
-    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN6_SMEM));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
+    EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc6<TRACE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
     attr_set = true;
   }
   auto go = [&](auto kern) -> int {
-    EO_CHECK_CUDA(launch_chain(kern, grid, dim3(ATTN5_THREADS), ATTN6_SMEM, st, pl->map, out, p.T, p.heads, p.ch, scale_log2,
+    EO_CHECK_CUDA(launch_chain(kern, grid, dim3(ATTN_THREADS), ATTN_SMEM, st, pl->map, out, p.T, p.heads, p.ch, scale_log2,
                                trace, trace_n));
     return EO_OK;
   };
@@ -951,23 +659,6 @@ static int attn6_launch(const TcAttnPlan* pl, int B, cudaStream_t st, long long*
 }
 
 int tc_attn_launch(const TcAttnPlan* pl, int B, cudaStream_t st) {
-#ifdef EO_ATTN_V5     // A/B builds: the previous kernel
-  {
-    static bool attr5 = false;
-    if (!attr5) {
-      EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
-      EO_CHECK_CUDA(cudaFuncSetAttribute(k_attn_tc5<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN5_SMEM));
-      attr5 = true;
-    }
-    const TcAttnParams& p = pl->p;
-    float scale_log2 = (1.0f / sqrtf((float)p.ch)) * 1.4426950408889634f;
-    dim3 grid((unsigned)ceil_div(p.T, NT5 * QT), (unsigned)p.heads, (unsigned)B);
-    auto kern = k_attn_tc5<false, false>;
-    EO_CHECK_CUDA(launch_chain(kern, grid, dim3(ATTN5_THREADS), ATTN5_SMEM, st, pl->map, reinterpret_cast<__nv_bfloat16*>(p.out), p.T,
-                               p.heads, p.ch, scale_log2, (long long*)nullptr, 0));
-    return EO_OK;
-  }
-#endif
 #ifdef EO_DEVTOOLS
   if (g_attn_trace) return attn6_launch<true>(pl, B, st, g_attn_trace, g_attn_trace_n);
 #endif

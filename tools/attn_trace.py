@@ -32,8 +32,8 @@ def run(B, T, heads, ch):
     life = np.median(t[:, 0])
     f = lambda c: np.median(t[:, c]) / nb
     print(f"attention B={B} T={T} heads={heads} ch={ch}: {len(t)} CTAs traced, {nb:.0f} half-blocks, CTA life {life:.0f} clk "
-          f"= {life / nb:.0f} clk per 64 keys\n   per 64 keys, softmax warp (tile 0): waits S {f(1):.0f}, wait::ld+max(next) {f(2):.0f}, vote(+raise) {f(3):.0f}, "
-          f"exp+pack {f(4):.0f}, st+hand-over {f(5):.0f}; issuer 0 waits P {f(6):.0f}")
+          f"= {life / nb:.0f} clk per 64 keys\n   per 64 keys: softmax warp (tile 0, quadrant 0) spins on S {f(1):.0f}; issuer 0 waits for P {f(6):.0f}"
+          f"   (phase by phase: tools/attn_timeline.py)")
 
 if __name__ == "__main__":
     if len(sys.argv) > 4:
