@@ -562,26 +562,38 @@ k_chan_stats(const __nv_bfloat16* __restrict__ x, int C, int HW, int ppc, double
   for (int i = tid; i < 2 * C; i += blockDim.x) atomicAdd(stats + (long long)b * C * 2 + i, sm[i]);
 }
 
-// GroupNorm scale/shift from per-channel sums of one or two concatenated tensors
-__global__ void k_gn_finalize_ch(const double* __restrict__ sa, int Ca, const double* __restrict__ sb, int Cb,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta, int B,
-                                 int HW, float* __restrict__ scale, float* __restrict__ shift) {
+// GroupNorm scale/shift from per-channel sums of one or two concatenated tensors.  One thread per channel, a block
+// holds gpb whole groups of cpg channels: every thread fetches its own (sum, sum of squares) -- ONE load per thread,
+// all in flight together; the kernel used to walk the cpg channels of its group with dependent loads, 7 us per launch
+// 56 times per forward -- parks it in shared memory, and adds up its group in channel order (the order of the
+// sequential sum it replaces: bit-identical rows).
+__global__ void __launch_bounds__(256)
+k_gn_finalize_ch(const double* __restrict__ sa, int Ca, const double* __restrict__ sb, int Cb,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, int B,
+                 int HW, int cpg, int gpb, float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ double2 sm[256];
   pdl_wait(); pdl_trigger();
   const int C = Ca + Cb;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * C) return;
-  const int b = i / C, c = i - b * C;
-  const int cpg = C / 32, g0 = (c / cpg) * cpg;
-  double s = 0.0, q = 0.0;
-  for (int k = g0; k < g0 + cpg; ++k) {
-    const double* src = k < Ca ? sa + ((long long)b * Ca + k) * 2 : sb + ((long long)b * Cb + (k - Ca)) * 2;
-    s += src[0]; q += src[1];
+  const int tid = threadIdx.x;
+  const int gl = tid / cpg, k = tid - gl * cpg;          // group inside the block, channel inside the group
+  const long long gi = (long long)blockIdx.x * gpb + gl;   // (image, group) pair
+  const bool on = gl < gpb && gi < (long long)B * 32;
+  const int b = (int)(gi >> 5), c = (int)(gi & 31) * cpg + k;
+  if (on) {
+    const double* src = c < Ca ? sa + ((long long)b * Ca + c) * 2 : sb + ((long long)b * Cb + (c - Ca)) * 2;
+    sm[tid] = *reinterpret_cast<const double2*>(src);
   }
+  __syncthreads();
+  if (!on) return;
+  double s = 0.0, q = 0.0;
+  const double2* grp = sm + gl * cpg;
+  for (int j = 0; j < cpg; ++j) { s += grp[j].x; q += grp[j].y; }
   const double n = (double)cpg * (double)HW;
   const double mean = s / n;
   double var = q / n - mean * mean;
   if (var < 0.0) var = 0.0;
   const double rstd = 1.0 / sqrt(var + 1e-5);
+  const long long i = (long long)b * C + c;
   scale[i] = (float)(rstd * (double)gamma[c]);
   shift[i] = (float)((double)beta[c] - mean * rstd * (double)gamma[c]);
 }
@@ -706,9 +718,11 @@ int launch_chan_stats(const void* x_bf16, int B, int HW, int C, double* stats, c
 
 int launch_gn_finalize_ch(const double* sa, int Ca, const double* sb, int Cb, const float* gamma, const float* beta,
                           int B, int HW, float* scale, float* shift, cudaStream_t st) {
-  EO_REQUIRE((Ca + Cb) % 32 == 0, EO_ERR_ARG, "gn_finalize_ch: channels %d not divisible by 32", Ca + Cb);
-  EO_CHECK_CUDA(launch_chain(k_gn_finalize_ch, dim3((unsigned)ceil_div((long long)B * (Ca + Cb), 256)), dim3(256), 0, st, sa, Ca,
-                             sb, Cb, gamma, beta, B, HW, scale, shift));
+  const int C = Ca + Cb;
+  EO_REQUIRE(C % 32 == 0 && C / 32 <= 256, EO_ERR_ARG, "gn_finalize_ch: %d channels (a multiple of 32, at most 8192)", C);
+  const int cpg = C / 32, gpb = 256 / cpg;      // whole groups per 256-thread block
+  EO_CHECK_CUDA(launch_chain(k_gn_finalize_ch, dim3((unsigned)ceil_div((long long)B * 32, gpb)), dim3(256), 0, st, sa, Ca,
+                             sb, Cb, gamma, beta, B, HW, cpg, gpb, scale, shift));
   return EO_OK;
 }
 
@@ -1203,9 +1217,14 @@ __global__ void __launch_bounds__(256)
 k_stem_im2col(const float* __restrict__ x, int Cx, const float* __restrict__ cond, int Cc, __nv_bfloat16* __restrict__ dst,
               int H, int W, long long npix) {
   // one thread per pixel: 9 C coalesced loads (neighbouring threads read neighbouring pixels of an NCHW row),
-  // 64 bf16 built in registers, eight 16-byte stores
+  // 64 bf16 built in registers; the 128-byte pixel rows go through shared memory (16-byte chunk j of pixel p at
+  // position j ^ (p & 7)) so that a warp's store instruction covers 512 contiguous bytes (four whole pixels) instead
+  // of 32 half-filled sectors 128 bytes apart
+  __shared__ uint4 stage[256 * 8];
   const long long HW = (long long)H * W;
-  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+  const int tid = threadIdx.x;
+  for (long long pix0 = blockIdx.x * (long long)blockDim.x; pix0 < npix; pix0 += (long long)gridDim.x * blockDim.x) {
+    const long long pix = pix0 + tid < npix ? pix0 + tid : npix - 1;      // the tail recomputes the last pixel, stores are guarded
     const int b = (int)(pix / HW);
     const int r = (int)(pix - (long long)b * HW);
     const int oh = r / W, ow = r - oh * W;
@@ -1228,9 +1247,16 @@ k_stem_im2col(const float* __restrict__ x, int Cx, const float* __restrict__ con
       else if (k < 18 * C) f = v[k - 9 * C] - __bfloat162float(__float2bfloat16_rn(v[k - 9 * C]));
       e[k] = __float2bfloat16_rn(f);
     }
-    uint4* o = reinterpret_cast<uint4*>(dst + pix * 64);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = reinterpret_cast<const uint4*>(e)[j];
+    for (int j = 0; j < 8; ++j) stage[tid * 8 + (j ^ (tid & 7))] = reinterpret_cast<const uint4*>(e)[j];
+    __syncthreads();
+    uint4* o = reinterpret_cast<uint4*>(dst + pix0 * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = i * 32 + (tid >> 3), j = tid & 7;       // pixel inside the block, chunk
+      if (pix0 + p < npix) o[p * 8 + j] = stage[p * 8 + (j ^ (p & 7))];
+    }
+    __syncthreads();
   }
 }
 // 4..32 input channels: cat(x, cond) (NCHW fp32) -> one 64-channel bf16 NHWC pixel, channels [0, C) the values
