@@ -28,6 +28,7 @@ posterior update + next step's 'sum' conditioning mix.  images/sec = images in f
 from __future__ import annotations
 
 import argparse
+import contextlib
 import gc
 import json
 import math
@@ -180,11 +181,12 @@ def cpu_reference_steps(size, batch, steps, warmup):
         RefDiffusion, RefUNet, _, ref_mod = ref
         torch.manual_seed(1234)
         unet = randomize_zero_init_(RefUNet(image_size=size, **ARCH)).eval()
-        diff = RefDiffusion(unet, size, 3, timesteps=warmup + steps, cond_type="sum").eval()
+        with contextlib.redirect_stdout(sys.stderr):     # the reference prints "loading model..." / "Loaded!!": stdout carries the JSON line only
+            diff = RefDiffusion(unet, size, 3, timesteps=warmup + steps, cond_type="sum").eval()
         ref_mod.save_image = lambda *a, **k: None        # sampling() writes PNGs unconditionally
         stamps = []
         h = unet.register_forward_pre_hook(lambda m, a: stamps.append(time.perf_counter()))
-        with torch.no_grad():
+        with torch.no_grad(), contextlib.redirect_stdout(sys.stderr):
             diff.sampling(batch, clipped_reverse_diffusion=True, device="cpu", cond=cond)
         stamps.append(time.perf_counter())
         h.remove()
