@@ -502,13 +502,18 @@ struct eo_unet {
     TcSegSpec s; s.act = a; s.ntaps = 1; s.dh[0] = 0; s.dw[0] = 0; s.plane[0] = 0;
     return s;
   }
-  // a plain 3x3 window over one tensor: served from halo patches when the output grid allows it
-  static bool patchable(const TcSegSpec& s, int Ho, int Wo) {
-    if (s.ntaps != 9 || s.stride != 1 || !tc_conv_patch_supported(Ho, Wo)) return false;
-    for (int t = 0; t < 9; ++t)
-      if (s.dh[t] != t / 3 - 1 || s.dw[t] != t % 3 - 1 || s.plane[t] != 0) return false;
-    return true;
+  // a plain 3x3 window over one tensor -- or a 2x2 corner of it, the taps of a sub-pixel convolution of Upsample --
+  // is served from halo patches when the output grid allows it: the tc_patch_code of the window, 0 = plain tiles
+  static int patch_code(const TcSegSpec& s, int Ho, int Wo) {
+    if (s.stride != 1 || !tc_conv_patch_supported(Ho, Wo) || (s.ntaps != 9 && s.ntaps != 4)) return 0;
+    const int n = s.ntaps == 9 ? 3 : 2;
+    const int r0 = s.dh[0] + 1, c0 = s.dw[0] + 1;
+    if (r0 < 0 || c0 < 0 || r0 + n > 3 || c0 + n > 3) return 0;
+    for (int t = 0; t < s.ntaps; ++t)
+      if (s.dh[t] != r0 + t / n - 1 || s.dw[t] != c0 + t % n - 1 || s.plane[t] != 0) return 0;
+    return tc_patch_code(r0, n, c0, n);
   }
+  static bool patchable(const TcSegSpec& s, int Ho, int Wo) { return patch_code(s, Ho, Wo) != 0; }
   // weights of a patch segment are K-ordered (64-channel block, tap, channel): one PackSeg per block
   static std::vector<PackSeg> patch_order(const std::vector<PackSeg>& segs, const std::vector<bool>& patch) {
     std::vector<PackSeg> o;
@@ -528,7 +533,11 @@ struct eo_unet {
                    const Act* residual, int Ho, int Wo, Act* out, cudaStream_t st, bool want_stats = true,
                    const OutView* view = nullptr, double alg_flops = -1.0, int nchw_C = 0) {
     std::vector<bool> patch;
-    for (auto& ts : tsegs) patch.push_back(patchable(ts, Ho, Wo) && ts.act.C % 64 == 0);
+    std::vector<int> pcode;
+    for (auto& ts : tsegs) {
+      pcode.push_back(ts.act.C % 64 == 0 ? patch_code(ts, Ho, Wo) : 0);
+      patch.push_back(pcode.back() != 0);
+    }
     const std::vector<PackSeg> segs = patch_order(segs_in, patch);
     void* Wp = nullptr; int K = 0;
     int rc = pack_tc(segs, Cout_rows, d_row_map, &Wp, &K, st);
@@ -554,7 +563,7 @@ struct eo_unet {
       p.nseg = (int)tv.size();
       for (int i = 0; i < p.nseg; ++i) {
         p.seg[i].ptr = ptr(tv[i].act.off); p.seg[i].C = tv[i].act.C;
-        p.seg[i].Bt = Bmax * tv[i].batch_mult; p.seg[i].ntaps = tv[i].ntaps; p.seg[i].patch = patch[i] ? 1 : 0;
+        p.seg[i].Bt = Bmax * tv[i].batch_mult; p.seg[i].ntaps = tv[i].ntaps; p.seg[i].patch = pcode[i];
         p.seg[i].stride = tv[i].stride;
         if (tv[i].has_gn) {
           p.seg[i].gn_scale = ptr<float>(tv[i].gn.scale_off); p.seg[i].gn_shift = ptr<float>(tv[i].gn.shift_off);
@@ -1617,7 +1626,7 @@ int eo_test_conv_tc(const void* x_bf16, const float* w, const float* bias, const
       p.seg[0].dw[t] = (int8_t)(k == 3 ? t % 3 - 1 : 0);
       p.seg[0].dn[t] = 0;
     }
-    p.seg[0].patch = patch ? 1 : 0;
+    p.seg[0].patch = patch ? TC_PATCH_3X3 : 0;
     // development aid (tools/conv_check.py): EO_TEST_GN=1 folds an identity GroupNorm affine (scale 1,
     // shift 0) into the operand load, =2 adds the SiLU (the caller then compares against conv(silu(x)))
 #ifdef EO_DEVTOOLS

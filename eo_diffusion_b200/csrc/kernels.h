@@ -155,6 +155,8 @@ int launch_scale_cols_bf16(void* x, long long rows, int ld, int col0, int ncols,
 // ---------------------------------------------------------------------------------------
 // tcgen05 tensor-core kernels (tc_conv.cu / tc_attn.cu)
 // ---------------------------------------------------------------------------------------
+constexpr int tc_patch_code(int r0, int nr, int c0, int nc) { return 1 | (r0 << 4) | (nr << 8) | (c0 << 12) | (nc << 16); }
+constexpr int TC_PATCH_3X3 = tc_patch_code(0, 3, 0, 3);
 struct TcConvSeg {
   const void* ptr = nullptr;  // bf16 NHWC [Bt, H, W, C]  (Bt may be 4*B for space-to-depth planes)
   int C = 0;
@@ -167,8 +169,11 @@ struct TcConvSeg {
   const float* gn_scale = nullptr;   // [B, gn_ld]
   const float* gn_shift = nullptr;
   int gn_ld = 0, gn_coff = 0, silu = 0;
-  int patch = 0;              // a plain 3x3 window served from one halo patch per 64 channels; the
-                              // segment's weights are then K-ordered (64-channel block, tap, channel)
+  int patch = 0;              // taps served from ONE halo patch per 64 channels: tc_patch_code(r0, nr, c0, nc) = the
+                              // rows r0 .. r0+nr-1 and columns c0 .. c0+nc-1 of the 3x3 neighbourhood, tap t at
+                              // (dh, dw) = (r0 + t / nc - 1, c0 + t % nc - 1) -- TC_PATCH_3X3 for a plain 3x3 conv, a
+                              // 2x2 corner for a sub-pixel convolution of Upsample; the segment's weights are then
+                              // K-ordered (64-channel block, tap, channel).  0 = plain 128-pixel tiles, one per tap
   int stride = 1;             // 2: the segment's grid is [Bt, 2H, 2W, C] and output pixel (h, w) reads source pixel
                               // (2h + dh, 2w + dw): a stride-2 convolution straight from the full-resolution tensor
                               // (tensor map with traversal stride 2), no space-to-depth copy

@@ -241,8 +241,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         __syncwarp();
         if (!en.gn) ra.next((uint32_t)SAR);
         // weight tiles of this load: 9 for a patch (TPB per stage), 1 otherwise
-        const int nb = en.patch ? 9 : 1;
-        const int per = en.patch ? TPB : 1;
+        const int pnc = (en.patch >> 16) & 15;                         // columns of the patch's tap window
+        const int nb = en.patch ? ((en.patch >> 8) & 15) * pnc : 1;
+        const int per = en.patch ? (TPB > 1 ? pnc : 1) : 1;             // TPB > 1: one kernel row of taps per stage
         for (int j = 0; j < nb; j += per) {
           { TRACE_T0(); tc::mbar_wait(&b_empty[rb.i], rb.ph ^ 1); TRACE_ACC(tr_wait); }
           if (tc::elect_one()) {
@@ -269,7 +270,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       Ring ra, rg, rb;
       uint32_t it = 0;
       long long tr_ops = 0, tr_acc = 0, tr_a = 0;
-      int pg_next = tab[0].patch | (tab[0].gn << 8);      // (patch, gn) of the next entry, read one entry ahead
+      int pg_next = tab[0].gn | (tab[0].patch << 4);      // (patch, gn) of the next entry, read one entry ahead
       for (int w = cid; w < n_work; w += ncl, ++it) {
         const uint32_t ab = it & 1;
         { TRACE_T0(); tc::mbar_wait_cluster(&tmem_empty[ab], ((it >> 1) & 1) ^ 1); TRACE_ACC(tr_acc); }   // both CTAs' epilogues drained this buffer
@@ -277,9 +278,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         const uint32_t d_tmem = tmem_base + ab * ACC_STRIDE;
         uint32_t acc = 0;
         for (int e = 0; e < nent; ++e) {
-          const int patch = pg_next & 0xff;
-          const bool gn = (pg_next >> 8) != 0;
-          { const int e1 = e + 1 == nent ? 0 : e + 1; pg_next = tab[e1].patch | (tab[e1].gn << 8); }
+          const int patch = pg_next >> 4;
+          const bool gn = (pg_next & 15) != 0;
+          { const int e1 = e + 1 == nent ? 0 : e + 1; pg_next = tab[e1].gn | (tab[e1].patch << 4); }
           {
             TRACE_T0();
             if (gn) tc::mbar_wait_cluster(&g_ready[rg.i], rg.ph);
@@ -317,7 +318,17 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           if (patch) {
             // tap (kh, kw) of a patch starts kh patch rows + kw pixels into it
             const uint64_t ad0 = tc::make_sw128_desc_sbo(a_base, PATCH_W * 128);
-            if (TPB == 3) {
+            if (patch != TC_PATCH_3X3) {
+              // a sub-window of the 3x3 neighbourhood (the 2x2 corner of a sub-pixel convolution): same patch, fewer taps
+              const int r0 = (patch >> 4) & 15, nr = (patch >> 8) & 15, c0 = (patch >> 12) & 15, nc = (patch >> 16) & 15;
+              if (TPB == 3) {
+                for (int kh = 0; kh < nr; ++kh) kgroup(ad0 + (uint64_t)(((r0 + kh) * PATCH_W + c0) * 8), 8u, nc, kh == nr - 1);
+              } else {
+                for (int kh = 0; kh < nr; ++kh)
+                  for (int kw = 0; kw < nc; ++kw)
+                    kgroup(ad0 + (uint64_t)(((r0 + kh) * PATCH_W + c0 + kw) * 8), 0u, 1, kh == nr - 1 && kw == nc - 1);
+              }
+            } else if (TPB == 3) {
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) kgroup(ad0 + (uint64_t)(kh * PATCH_W * 8), 8u, 3, kh == 2);
             } else {
@@ -820,14 +831,16 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
     uint64_t str[3] = {(uint64_t)sg.C * 2, sW * sg.C * 2, sH * sW * sg.C * 2};
     uint32_t box[4] = {(uint32_t)BK, (uint32_t)(g.bw * sg.stride), (uint32_t)(g.bh * sg.stride), (uint32_t)g.bn};
     uint32_t est[4] = {1u, (uint32_t)sg.stride, (uint32_t)sg.stride, 1u};
-    EO_REQUIRE(!sg.gn_scale || sg.patch, EO_ERR_ARG, "tc_conv3: GroupNorm can only be folded into a halo-patch segment");
+    EO_REQUIRE(!sg.gn_scale || sg.patch == TC_PATCH_3X3, EO_ERR_ARG, "tc_conv3: GroupNorm can only be folded into a 3x3 halo-patch segment");
     EO_REQUIRE(!sg.gn_scale || (sg.gn_shift && sg.gn_ld % 4 == 0 && sg.gn_coff % 8 == 0), EO_ERR_ARG,
                "tc_conv3: GroupNorm rows must be 16-byte aligned");
+    const int pr0 = (sg.patch >> 4) & 15, pnr = (sg.patch >> 8) & 15, pc0 = (sg.patch >> 12) & 15, pnc = (sg.patch >> 16) & 15;
     if (sg.patch) {
-      EO_REQUIRE(sg.ntaps == 9, EO_ERR_ARG, "tc_conv3: a patch segment has nine taps");
-      for (int t = 0; t < 9; ++t)
-        EO_REQUIRE(sg.dh[t] == t / 3 - 1 && sg.dw[t] == t % 3 - 1 && sg.dn[t] == 0, EO_ERR_ARG,
-                   "tc_conv3: a patch segment is a plain 3x3 window");
+      EO_REQUIRE(pnr >= 1 && pnc >= 1 && pr0 + pnr <= 3 && pc0 + pnc <= 3 && sg.ntaps == pnr * pnc, EO_ERR_ARG,
+                 "tc_conv3: a patch segment takes a window of the 3x3 neighbourhood (code %#x, %d taps)", sg.patch, sg.ntaps);
+      for (int t = 0; t < sg.ntaps; ++t)
+        EO_REQUIRE(sg.dh[t] == pr0 + t / pnc - 1 && sg.dw[t] == pc0 + t % pnc - 1 && sg.dn[t] == 0, EO_ERR_ARG,
+                   "tc_conv3: the taps of a patch segment walk its window row by row");
       box[1] = PATCH_W; box[2] = PATCH_H; box[3] = 1;
     }
     int rc = encode_tmap_bf16(&pl->mapA[s], sg.ptr, 4, dims, str, box, est);
@@ -835,10 +848,10 @@ int tc_conv3_plan_fill(const TcConvParams& p, TcConvPlan* pl) {
     if (sg.patch) {
       // K order of a patch segment: (64-channel block, tap, channel)
       for (int c0 = 0; c0 < sg.C; c0 += BK) {
-        KEnt3 e{}; e.seg = s; e.c0 = c0; e.patch = 1; e.kofs = kofs; e.sc = 1;
+        KEnt3 e{}; e.seg = s; e.c0 = c0; e.patch = sg.patch; e.kofs = kofs; e.sc = 1;
         e.gn = sg.gn_scale ? (sg.silu ? 2 : 1) : 0; e.gnc = sg.gn_coff + c0;
         tab.push_back(e);
-        kofs += 9 * BK;
+        kofs += pnr * pnc * BK;
       }
     } else {
       for (int t = 0; t < sg.ntaps; ++t)
