@@ -39,6 +39,34 @@ def test_psnr_known_answers():
     assert math.isinf(float(P.psnr(a, a)))
 
 
+def test_psnr_and_ssim_reproduce_torchmetrics_published_examples():
+    """The only torchmetrics outputs available without the package: the known-answer examples printed in the
+    docstrings of torchmetrics.functional.peak_signal_noise_ratio (`tensor(2.5527)`) and
+    structural_similarity_index_measure (`preds = torch.rand([3, 3, 256, 256]); target = preds * 0.75` ->
+    `tensor(0.9219)`; data_range=None = the larger of the two value ranges).  The SSIM of that pair is a
+    property of the uniform distribution, not of the seed (spread 1e-6 over seeds), so the printed four digits
+    pin the restatement whatever generator state the docs were built with."""
+    pred = torch.tensor([[0.0, 1.0], [2.0, 3.0]])
+    target = torch.tensor([[3.0, 2.0], [1.0, 0.0]])
+    assert round(float(P.psnr(pred, target, data_range=3.0)), 4) == 2.5527      # data_range=None: target.max - target.min
+    for seed in (42, 0, 7):
+        torch.manual_seed(seed)
+        preds = torch.rand([3, 3, 256, 256])
+        tgt = preds * 0.75
+        dr = max(float(preds.max() - preds.min()), float(tgt.max() - tgt.min()))
+        assert round(float(P.ssim(preds, tgt, data_range=dr)), 4) == 0.9219
+
+
+def test_psnr_matches_opencv():
+    """cv2.PSNR(a, b, R): an independent published implementation (OpenCV core) of the same definition."""
+    cv2 = pytest.importorskip("cv2")
+    g = torch.Generator().manual_seed(11)
+    a = torch.rand((3, 48, 40), generator=g)
+    b = (a + 0.05 * torch.randn((3, 48, 40), generator=g)).clamp(0, 1)
+    for R in (1.0, 2.0):
+        assert float(P.psnr(a, b, data_range=R)) == pytest.approx(cv2.PSNR(a.numpy(), b.numpy(), R), abs=1e-4)
+
+
 def _ssim_scipy(x, y, data_range=1.0):
     ndi = pytest.importorskip("scipy.ndimage")
     w = np.exp(-0.5 * (np.arange(-5, 6) / 1.5) ** 2)
