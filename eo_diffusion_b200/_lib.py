@@ -71,6 +71,7 @@ SIGNATURES = {
     "eo_sample_ddpm": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "eo_post_map": (_I, [_P, _P, _L, _I, _F, _P]),
     "eo_post_dim_masked": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "eo_post_grid_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _I, C.POINTER(_I), _P]),
     "eo_post_stats": (_I, [_P, _L, _P, _P, _P]),
     "eo_psnr": (_I, [_P, _P, _L, _F, _P, _P, _P]),
     "eo_ssim": (_I, [_P, _P, _I, _I, _I, _I, _F, C.POINTER(_F), _P, _P, _P, _P]),

@@ -5,9 +5,12 @@
 //   torchvision adjust_brightness(x, 3) = (3 * x).clamp(0, 1) for floats     :141-142, :149
 //   image.min(), x.mean() (the host branches on them)                        :128, :141, :149
 //   torchmetrics peak_signal_noise_ratio / structural_similarity_index_measure(data_range=1.0)   :138
+//   torchvision save_image(x, path, nrow=...) = make_grid + `mul(255).add_(0.5).clamp_(0, 255).to(uint8)`   :143-150,
+//     and inside the sampling loop itself, diffusion/model.py:62-66 (`save_image((x_t + 1.) / 2., ...)`)
 // The elementwise passes are bit-exact with the fp32 torch ops (round-to-nearest intrinsics, no FMA
 // contraction).  PSNR and SSIM follow the published torchmetrics algorithms (torchmetrics is not part of
-// the reference checkout: its arithmetic is restated in oracle/postprocess.py, parity unpinned):
+// the reference checkout: its arithmetic is restated in oracle/postprocess.py and pinned to four digits on the
+// library's published docstring examples):
 //   PSNR = 10 log10(data_range^2 / mean((a - b)^2)) over the whole batch;
 //   SSIM: 11 x 11 Gaussian window (sigma 1.5) over reflect-padded images, the padded border cropped again,
 //         i.e. exactly the windows that lie inside the image; c1 = (0.01 R)^2, c2 = (0.03 R)^2; mean per image,
@@ -45,6 +48,37 @@ k_post_dim(const float* __restrict__ image, const float* __restrict__ mask, floa
     float m = __fadd_rn(mask[b * HW + p], 0.7f);
     m = m < 0.f ? 0.f : (m > 1.f ? 1.f : m);
     out[i] = __fmul_rn(image[i], m);
+  }
+}
+
+// torchvision.utils.make_grid (padding, pad_value; a single-channel batch is repeated to three channels; ONE image is
+// returned as it is, without a border) followed by save_image's quantisation, written as the HWC uint8 array
+// PIL.Image.fromarray takes.  PRE 1 applies (x + 1) / 2 first (model.py:63).  One thread per grid pixel.
+template <int PRE>
+__global__ void __launch_bounds__(256)
+k_post_grid_u8(const float* __restrict__ x, unsigned char* __restrict__ out, int B, int C, int H, int W, int Cg,
+               int xmaps, int pad, int GH, int GW, float pad_value) {
+  const long long npix = (long long)GH * GW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    const int gy = (int)(i / GW), gx = (int)(i % GW);
+    const int cell_h = H + pad, cell_w = W + pad;
+    const int ry = gy - pad, rx = gx - pad;                 // position relative to the first image's corner
+    int k = -1, iy = 0, ix = 0;
+    if (ry >= 0 && rx >= 0) {
+      const int my = ry / cell_h, mx = rx / cell_w;
+      iy = ry - my * cell_h; ix = rx - mx * cell_w;
+      if (iy < H && ix < W && mx < xmaps && my * xmaps + mx < B) k = my * xmaps + mx;
+    }
+    for (int c = 0; c < Cg; ++c) {
+      float v = pad_value;
+      if (k >= 0) {
+        v = x[(((long long)k * C + (C == 1 ? 0 : c)) * H + iy) * W + ix];
+        if (PRE == 1) v = __fmul_rn(__fadd_rn(v, 1.0f), 0.5f);
+      }
+      v = __fadd_rn(__fmul_rn(v, 255.0f), 0.5f);
+      v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
+      out[i * Cg + c] = (unsigned char)__float2int_rz(v);
+    }
   }
 }
 
@@ -208,6 +242,29 @@ int eo_post_dim_masked(const float* image, const float* mask, float* out, int B,
   EO_REQUIRE(image && mask && out && B > 0 && C > 0 && HW > 0, EO_ERR_ARG, "eo_post_dim_masked: bad argument");
   const long long n = (long long)B * C * HW;
   k_post_dim<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(image, mask, out, C, HW, n);
+  EO_CHECK_LAUNCH();
+  return EO_OK;
+}
+
+int eo_post_grid_u8(const float* x, unsigned char* out, int B, int C, int H, int W, int nrow, int padding, float pad_value,
+                    int pre, int* grid_hw_or_null, void* stream) {
+  EO_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && nrow > 0 && padding >= 0, EO_ERR_ARG, "eo_post_grid_u8: bad geometry");
+  EO_REQUIRE(pre == 0 || pre == 1, EO_ERR_ARG, "eo_post_grid_u8: pre %d (0 none, 1 (x+1)/2)", pre);
+  // make_grid: one image comes back unpadded; otherwise xmaps = min(nrow, B) columns, ceil(B / xmaps) rows of
+  // (H + padding) x (W + padding) cells plus one more border on the far sides
+  const int pad = B == 1 ? 0 : padding;
+  const int xmaps = nrow < B ? nrow : B;
+  const int ymaps = (B + xmaps - 1) / xmaps;
+  const long long GH = B == 1 ? H : (long long)(H + pad) * ymaps + pad, GW = B == 1 ? W : (long long)(W + pad) * xmaps + pad;
+  EO_REQUIRE(GH <= INT32_MAX && GW <= INT32_MAX, EO_ERR_ARG, "eo_post_grid_u8: grid too large");
+  if (grid_hw_or_null) { grid_hw_or_null[0] = (int)GH; grid_hw_or_null[1] = (int)GW; grid_hw_or_null[2] = C == 1 ? 3 : C; }
+  if (!x && !out) return EO_OK;                         // geometry query
+  EO_REQUIRE(x && out, EO_ERR_ARG, "eo_post_grid_u8: null pointer");
+  const int Cg = C == 1 ? 3 : C;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = grid_for(GH * GW, 256);
+  if (pre == 0) k_post_grid_u8<0><<<g, 256, 0, st>>>(x, out, B, C, H, W, Cg, xmaps, pad, (int)GH, (int)GW, pad_value);
+  else k_post_grid_u8<1><<<g, 256, 0, st>>>(x, out, B, C, H, W, Cg, xmaps, pad, (int)GH, (int)GW, pad_value);
   EO_CHECK_LAUNCH();
   return EO_OK;
 }

@@ -213,9 +213,9 @@ class EODiffusion(nn.Module):
 
     def _write_pngs(self, x_t, gt, mask, noise, t, i, idx, n):
         # model.py:62-66 (the reference raises FileNotFoundError if ./results/prova is missing)
-        from torchvision.utils import save_image
+        from .postprocess import save_image     # torchvision's save_image, grid + quantisation on the device
         nrow = int(math.sqrt(n))
-        save_image((x_t + 1.) / 2., f"results/prova/s{idx}_{i}_pred.png", nrow=nrow)
+        save_image(x_t, f"results/prova/s{idx}_{i}_pred.png", nrow=nrow, signed=True)
         if self.cond_type == "sum":
             gt_noised = self._forward_diffusion(gt, t, noise)
             save_image(mask * gt_noised, f"results/prova/s{i}_masked.png", nrow=nrow)

@@ -1,6 +1,7 @@
 """On-device post-processing and metrics of finished samples: what reference
 `inference.py:128-150` does on the CPU/GPU with torch, torchvision and torchmetrics after `sampling()` returns
--- range mapping, the dimmed conditioning image, brightness adjustment, PSNR and SSIM -- as libeo_b200 kernels.
+-- range mapping, the dimmed conditioning image, brightness adjustment, PSNR and SSIM, and the device half of
+torchvision's `save_image` (grid + uint8 quantisation, so 3 bytes per pixel leave the GPU) -- as libeo_b200 kernels.
 Function names follow the libraries the reference calls (`peak_signal_noise_ratio`,
 `structural_similarity_index_measure`, `adjust_brightness`).  CUDA tensors only; there is no CPU fallback."""
 from __future__ import annotations
@@ -12,7 +13,7 @@ import torch
 from . import _lib
 
 __all__ = ["peak_signal_noise_ratio", "structural_similarity_index_measure", "adjust_brightness",
-           "to_unit_range", "dim_masked", "tensor_stats", "postprocess_samples"]
+           "to_unit_range", "dim_masked", "tensor_stats", "postprocess_samples", "make_grid_u8", "save_image"]
 
 
 def _f32(t, name):
@@ -64,6 +65,38 @@ def dim_masked(image, mask):
         _lib.check(_lib.lib().eo_post_dim_masked(_lib.ptr(image), _lib.ptr(mask), _lib.ptr(out), B, Cc, hw,
                                                  _lib.stream_ptr()), "eo_post_dim_masked")
     return out
+
+
+def make_grid_u8(tensor, nrow: int = 8, padding: int = 2, pad_value: float = 0.0, signed: bool = False) -> torch.Tensor:
+    """`torchvision.utils.make_grid(tensor, nrow, padding, pad_value=pad_value)` followed by `save_image`'s
+    `mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8)`: a [GH, GW, C] uint8 DEVICE tensor,
+    bit-identical to torchvision's.  `signed=True` maps (x + 1) / 2 first (model.py:63).  Accepts what
+    `save_image` is given on this path: [B,C,H,W], [C,H,W] or [H,W] float tensors."""
+    _lib.require_cuda_tensor(tensor, "tensor")
+    if tensor.dim() == 2:
+        tensor = tensor[None]
+    if tensor.dim() == 3:
+        tensor = tensor[None]
+    if tensor.dim() != 4:
+        raise ValueError(f"make_grid_u8 takes [B,C,H,W], [C,H,W] or [H,W]; got {tuple(tensor.shape)}")
+    x = tensor.detach().float().contiguous()
+    B, Cc, H, W = x.shape
+    geo = (C.c_int * 3)()
+    L = _lib.lib()
+    args = (B, Cc, H, W, int(nrow), int(padding), float(pad_value), int(bool(signed)), geo)
+    _lib.check(L.eo_post_grid_u8(None, None, *args, None), "eo_post_grid_u8")
+    out = torch.empty((geo[0], geo[1], geo[2]), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(L.eo_post_grid_u8(_lib.ptr(x), _lib.ptr(out), *args, _lib.stream_ptr()), "eo_post_grid_u8")
+    return out
+
+
+def save_image(tensor, fp, format=None, nrow: int = 8, padding: int = 2, pad_value: float = 0.0, signed: bool = False) -> None:
+    """`torchvision.utils.save_image(tensor, fp, nrow=...)` (inference.py:143-150, model.py:62-66) with the grid and
+    the quantisation on the device: the uint8 grid is the only thing copied to the host; PIL writes the same file."""
+    from PIL import Image
+    grid = make_grid_u8(tensor, nrow=nrow, padding=padding, pad_value=pad_value, signed=signed)
+    Image.fromarray(grid.cpu().numpy()).save(fp, format=format)
 
 
 def peak_signal_noise_ratio(preds, target, data_range: float = 1.0) -> torch.Tensor:

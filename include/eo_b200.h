@@ -264,6 +264,15 @@ EO_API int eo_cfg_combine(const float* e_uncond, const float* e_cond, float scal
 EO_API int eo_post_map(const float* x, float* out, int64_t n, int mode, float factor, void* stream);
 /* out[b,c,p] = image[b,c,p] * clip(mask[b,0,p] + 0.7, 0, 1)   (inference.py:135) */
 EO_API int eo_post_dim_masked(const float* image, const float* mask, float* out, int B, int C, int HW, void* stream);
+/* torchvision.utils.save_image's device-side half (reference inference.py:143-150 and, inside the sampling loop,
+ * diffusion/model.py:62-66): make_grid(x [B,C,H,W], nrow, padding, pad_value) followed by
+ * `mul(255).add_(0.5).clamp_(0, 255).to(uint8)`, written as the HWC uint8 array PIL.Image.fromarray takes, so only
+ * 3 bytes per grid pixel cross PCIe.  Grid geometry as torchvision: one image comes back without a border, a
+ * single-channel batch is repeated to three channels.  pre = 1 applies (x + 1) / 2 first (model.py:63).
+ * grid_hw_or_null (HOST, 3 ints) receives {grid height, grid width, grid channels}; with x = out = NULL the call
+ * only answers that query.  Bit-exact with torchvision. */
+EO_API int eo_post_grid_u8(const float* x, unsigned char* out, int B, int C, int H, int W, int nrow, int padding,
+                    float pad_value, int pre, int* grid_hw_or_null, void* stream);
 /* out3 = {mean, min, max} of x (the values the reference's host branches read: image.min() :128,
  * gt.mean() / cond.mean() / samples.mean() :141-149).  workspace4: 4 doubles of device scratch. */
 EO_API int eo_post_stats(const float* x, int64_t n, double* workspace4, float* out3, void* stream);

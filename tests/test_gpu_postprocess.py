@@ -77,3 +77,46 @@ def test_postprocess_samples_vs_oracle(cuda_dev, signed, batch, cond_type):
         assert torch.equal(got[k].cpu(), want[k]), k
     assert float(got["ssim"]) == pytest.approx(float(want["ssim"]), abs=2e-5)
     assert float(got["psnr"]) == pytest.approx(float(want["psnr"]), abs=2e-4)
+
+
+def _tv_grid_u8(x, **kw):
+    # torchvision.utils.save_image's own lines (installed torchvision, CPU)
+    from torchvision.utils import make_grid
+    return make_grid(x, **kw).mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8)
+
+
+@pytest.mark.parametrize("shape, nrow, padding, pad_value", [
+    ((16, 3, 64, 64), 4, 2, 0.0),          # sampling(): nrow = int(sqrt(n))
+    ((5, 3, 33, 47), 8, 2, 0.0),           # fewer images than nrow: one ragged row
+    ((7, 3, 20, 24), 3, 2, 0.5),           # last row partly empty, grey border
+    ((1, 3, 40, 24), 1, 2, 0.0),           # one image: torchvision returns it without a border
+    ((6, 1, 16, 16), 2, 1, 1.0),           # single-channel batch repeated to three channels
+    ((4, 3, 32, 32), 2, 0, 0.0),           # no border at all
+])
+def test_grid_u8_is_torchvision_bit_exact(cuda_dev, shape, nrow, padding, pad_value):
+    g = torch.Generator().manual_seed(sum(shape) + nrow)
+    x = torch.rand(shape, generator=g) * 1.3 - 0.15          # values outside [0, 1] exercise the clamp
+    x.view(-1)[:512] = torch.arange(512, dtype=torch.float32) / 510.0      # .5 ties of the quantiser
+    got = G.make_grid_u8(x.to(cuda_dev), nrow=nrow, padding=padding, pad_value=pad_value)
+    want = _tv_grid_u8(x, nrow=nrow, padding=padding, pad_value=pad_value)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == tuple(want.shape)
+    assert torch.equal(got.cpu(), want)
+    xs = x * 2 - 1
+    got = G.make_grid_u8(xs.to(cuda_dev), nrow=nrow, padding=padding, pad_value=pad_value, signed=True)
+    assert torch.equal(got.cpu(), _tv_grid_u8((xs + 1.) / 2., nrow=nrow, padding=padding, pad_value=pad_value))
+
+
+def test_save_image_writes_the_file_torchvision_writes(cuda_dev, tmp_path):
+    from PIL import Image
+    from torchvision.utils import save_image
+    import numpy as np
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand((9, 3, 32, 32), generator=g)
+    save_image(x, str(tmp_path / "tv.png"), nrow=3)
+    G.save_image(x.to(cuda_dev), str(tmp_path / "eo.png"), nrow=3)
+    assert (tmp_path / "tv.png").read_bytes() == (tmp_path / "eo.png").read_bytes()
+    save_image(x[0, 0], str(tmp_path / "tv1.png"))                  # [H, W]
+    G.save_image(x[0, 0].to(cuda_dev), str(tmp_path / "eo1.png"))
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "tv1.png")), np.asarray(Image.open(tmp_path / "eo1.png")))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.make_grid_u8(x)

@@ -170,3 +170,20 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and "workload" in d["config"]
+
+
+def test_grid_geometry_query_matches_torchvision():
+    """eo_post_grid_u8 with null buffers only answers the grid geometry (host arithmetic, no launch): it must be
+    torchvision.utils.make_grid's."""
+    import ctypes as C
+    from torchvision.utils import make_grid
+    from eo_diffusion_b200 import _lib
+    L = _lib.lib()
+    geo = (C.c_int * 3)()
+    for B, Cc, H, W, nrow, pad in [(16, 3, 64, 64, 4, 2), (5, 3, 33, 47, 8, 2), (7, 3, 20, 24, 3, 2), (1, 3, 40, 24, 1, 2),
+                                   (6, 1, 16, 16, 2, 1), (4, 3, 32, 32, 2, 0), (1, 1, 8, 8, 8, 2)]:
+        assert L.eo_post_grid_u8(None, None, B, Cc, H, W, nrow, pad, 0.0, 0, geo, None) == 0
+        want = make_grid(torch.zeros(B, Cc, H, W), nrow=nrow, padding=pad).shape
+        assert (geo[2], geo[0], geo[1]) == tuple(want)
+    assert L.eo_post_grid_u8(None, None, 0, 3, 8, 8, 1, 2, 0.0, 0, geo, None) < 0
+    assert L.eo_post_grid_u8(None, None, 2, 3, 8, 8, 1, 2, 0.0, 2, geo, None) < 0
