@@ -9,6 +9,10 @@ timeout 1500 python -m pytest tests -m gpu -q -s -p no:cacheprovider > $out/pyte
 grep -E "parity|passed|failed" $out/pytest_${tag}.log | tail -40
 python bench.py --breakdown $out/bd_${tag}.json > $out/bench_${tag}.json 2> $out/bench_${tag}.err || { tail -20 $out/bench_${tag}.err; exit 1; }
 tail -c 600 $out/bench_${tag}.json
+for wl in c1 c2; do   # per-op breakdown of the launch-bound workloads
+  python bench.py --workload $wl --steps 50 --warmup 10 --no-cpu --no-secondary --short-e2e --breakdown $out/bd_${wl}_${tag}.json \
+    > $out/bench_${wl}_${tag}.json 2> $out/bench_${wl}_${tag}.err
+done
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-secondary --short-e2e"
 $CMD > $out/plain_${tag}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 900 --csv \
