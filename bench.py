@@ -668,6 +668,13 @@ def run_ours(args, wl):
                                    "steps_per_image": spi, "ms_per_step": ms2, "steps": k2, "batch_per_gpu": w2["batch"],
                                    "frac": fl2 * w2["batch"] / (ms2 * 1e-3) / 1e12 / peaks["tflops"],
                                    "gpu_launches_per_step": l2}
+                if name == "c1":
+                    # the reference's only published speed for this path (tqdm lines of the demo
+                    # notebook, EO_Diffusion.ipynb:249-279 -- RTX 4000, fp32 eager, incl. its PNG writes): other
+                    # hardware, so a note next to the line, never `vs_baseline`
+                    secondary[name]["published"] = {"it_per_s": 26.3, "source": "EO_Diffusion.ipynb:249-279 (RTX 4000, torch 1.13 "
+                                                    "fp32 eager, batch 1, 64x64, incl. save_image calls)",
+                                                    "ours_it_per_s": 1e3 / ms2, "ratio": (1e3 / ms2) / 26.3}
                 c2.close()
             except Exception as ex:      # a secondary line must not cost the headline
                 secondary[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
