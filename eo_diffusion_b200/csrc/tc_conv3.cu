@@ -52,7 +52,14 @@ constexpr int PATCH_W = 10, PATCH_H = 18;                  // halo patch of an 8
 constexpr int PATCH_BYTES = PATCH_W * PATCH_H * 128;       // 23040
 constexpr int PLAIN_BYTES = BM * 128;                      // 16384
 constexpr int A_STAGE = 23552;                             // 23 KB: PATCH_BYTES rounded up to 1 KB
-constexpr int SA_MAX = 4;                                  // operand-A stages: SAR filled by TMA + SAG by the transform warps
+constexpr int SA_MAX = 8;                                  // operand-A stages: SAR filled by TMA + SAG by the transform warps
+// A launch whose operand loads are all plain 128-pixel tiles (1x1 / stride-2 convolutions, 3x3 windows over maps that
+// take no halo patch) feeds only four K = 16 MMAs per 16 KB operand load: its K loop runs at the latency of a TMA load
+// divided by the loads in flight.  Such launches pack their stages at PLAIN_BYTES and split the shared memory evenly
+// between operand and weight stages (up to SA_MAX deep) instead of three 23 KB stages next to twelve weight stages.
+#ifndef EO_CONV_DEEP_RING
+#define EO_CONV_DEEP_RING 1
+#endif
 constexpr int STG_BYTES = BM * 128;                        // one 128-row x 64-channel bf16 tile
 constexpr int MAX_ENT = 176;
 constexpr int MAX_XENT = 32;                               // GroupNorm-folded patch loads per tile (<= 2048 channels)
@@ -134,11 +141,11 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
            const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
            const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
            const KEnt3* __restrict__ ents, int nent, const XEnt3* __restrict__ xents, int n_xent, Geom3 g, int B, int BN,
-           int SB, int TPB, int SAR, int SAG, int n_work, int n_ntiles, Epi3 ep) {
+           int SB, int TPB, int SAR, int SAG, int a_stage, int n_work, int n_ntiles, Epi3 ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_a = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);   // operand-A stages
-  uint8_t* smem = smem_a + (SAR + SAG) * A_STAGE;                                    // everything else
-  uint8_t* smem_g = smem_a + SAR * A_STAGE;                                          // the transform warps' stages
+  uint8_t* smem = smem_a + (SAR + SAG) * a_stage;                                    // everything else (a_stage: A_STAGE, or PLAIN_BYTES for plain-tile launches)
+  uint8_t* smem_g = smem_a + SAR * a_stage;                                          // the transform warps' stages
   KEnt3* tab = reinterpret_cast<KEnt3*>(smem + Smem::TAB_OFF);
   XEnt3* xtab = reinterpret_cast<XEnt3*>(smem + Smem::XTAB_OFF);
   float* sstat = reinterpret_cast<float*>(smem + Smem::STAT_OFF);
@@ -226,7 +233,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           const int dh = (int)(short)(en.dhw & 0xffff), dw = en.dhw >> 16;
           const int cw = t.w0 * en.sc + (en.patch ? -1 : dw), chh = t.h0 * en.sc + (en.patch ? -1 : dh);
           const uint32_t bytes = en.patch ? PATCH_BYTES : PLAIN_BYTES;
-          uint8_t* dst = smem_a + ra.i * A_STAGE;
+          uint8_t* dst = smem_a + ra.i * a_stage;
           // one arrival per phase: the leader's producer, which posts the byte count of BOTH CTAs' loads
           if (rank == 0) tc::mbar_arrive_expect_tx(&r_full[ra.i], 2 * bytes);
           tc::tma2_load_4d(dst, ma, r_full_l + ra.i * 8, en.c0, cw, chh, t.n0 + en.dn);
@@ -288,7 +295,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             TRACE_ACC(tr_ops); TRACE_ACC(tr_a);
           }
           tc::tc_fence_after();
-          const uint32_t a_base = tc::smem_u32(gn ? smem_g + rg.i * A_STAGE : smem_a + ra.i * A_STAGE);
+          const uint32_t a_base = tc::smem_u32(gn ? smem_g + rg.i * a_stage : smem_a + ra.i * a_stage);
           uint64_t* a_release = gn ? &g_empty[rg.i] : &r_empty[ra.i];
           const bool last_e = e == nent - 1;
           // one weight stage: wait for it, issue the 4 K=16 MMAs of each of its NT 64-deep K blocks (tile u
@@ -474,7 +481,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       { TRACE_T0(); tc::mbar_wait(&g_empty[cur.ring.i], cur.ring.ph ^ 1); TRACE_ACC(tr_xw); }   // the MMAs that read this stage have retired
       const long long t_b0 = TRACE ? clock64() : 0;
       long long t_it = t_b0;
-      uint8_t* st = smem_g + cur.ring.i * A_STAGE;
+      uint8_t* st = smem_g + cur.ring.i * a_stage;
       // one bf16 pair: affine (+ SiLU) in fp32, back to bf16
       auto xf2 = [&](uint32_t in, uint64_t sc, uint64_t sh, bool act) -> uint32_t {
         uint64_t x = tc::fma2(tc::pack2(__uint_as_float(in << 16), __uint_as_float(in & 0xffff0000u)), sc, sh);
@@ -936,12 +943,19 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st, float* out_nch
   bool any_gn = false, any_raw = false;
   for (int s = 0; s < p.nseg; ++s) { if (p.seg[s].gn_scale) any_gn = true; else any_raw = true; }
   int SAR = any_raw ? (any_gn ? 2 : 3) : 0, SAG = any_gn ? (any_raw ? 2 : 3) : 0;
-  const int fixed = (SAR + SAG) * A_STAGE + Smem::VAR_OFF + (has_res ? 2 * STG_BYTES : 0);
   // narrow tiles: three weight tiles (one kernel row of a patch) per stage, see the MMA warp
   bool any_patch = false;
   for (int s = 0; s < p.nseg; ++s) any_patch |= p.seg[s].patch != 0;
   int TPB = (any_patch && BN <= 192) ? 3 : 1;
   const int b_stage = TPB * b_bytes;
+  int a_stage = A_STAGE;
+  if (EO_CONV_DEEP_RING && !any_patch && !any_gn) {
+    // plain tiles only: one weight tile per operand load, so as many (operand, weight) stage pairs as fit
+    a_stage = PLAIN_BYTES;
+    const int avail = SMEM_LIMIT - 1024 - Smem::VAR_OFF - (has_res ? 2 * STG_BYTES : 0);
+    SAR = std::max(3, std::min(SA_MAX, avail / (a_stage + b_stage)));
+  }
+  const int fixed = (SAR + SAG) * a_stage + Smem::VAR_OFF + (has_res ? 2 * STG_BYTES : 0);
   int SB = (SMEM_LIMIT - 1024 - fixed) / b_stage;
   if (SB > MAX_SB) SB = MAX_SB;
   EO_REQUIRE(SB >= 2, EO_ERR_STATE, "tc_conv3: shared memory budget leaves %d weight stages", SB);
@@ -997,7 +1011,7 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st, float* out_nch
   EO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA[0], pl->mapA[1], pl->mapA[2], pl->mapB, pl->mapOut,
                                    pl->mapRes, (const KEnt3*)pl->d_kblks, pl->nkb,
                                    (const XEnt3*)(reinterpret_cast<const uint8_t*>(pl->d_kblks) + pl->xent_off), pl->n_xent, g, B,
-                                   BN, SB, TPB, SAR, SAG, n_work, n_ntiles, ep));
+                                   BN, SB, TPB, SAR, SAG, a_stage, n_work, n_ntiles, ep));
   return EO_OK;
 }
 
