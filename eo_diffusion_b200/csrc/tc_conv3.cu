@@ -60,6 +60,15 @@ constexpr int SA_MAX = 8;                                  // operand-A stages: 
 #ifndef EO_CONV_DEEP_RING
 #define EO_CONV_DEEP_RING 1
 #endif
+// ... and, for tiles narrower than 256 channels, hand the MMA warp GROUPS of up to EO_CONV_GROUP_MAX such loads per
+// barrier round trip (one operand stage = the group's tiles side by side, one weight stage = its weight tiles): the
+// wait / fence / issue / commit chain around the four MMAs of a single 64-deep K block is longer than the MMAs themselves
+#ifndef EO_CONV_GROUP_MAX
+#define EO_CONV_GROUP_MAX 4
+#endif
+#ifndef EO_CONV_GROUP_STAGES
+#define EO_CONV_GROUP_STAGES 2       // stage pairs a group size must leave room for
+#endif
 constexpr int STG_BYTES = BM * 128;                        // one 128-row x 64-channel bf16 tile
 constexpr int MAX_ENT = 176;
 constexpr int MAX_XENT = 32;                               // GroupNorm-folded patch loads per tile (<= 2048 channels)
@@ -141,7 +150,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
            const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
            const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
            const KEnt3* __restrict__ ents, int nent, const XEnt3* __restrict__ xents, int n_xent, Geom3 g, int B, int BN,
-           int SB, int TPB, int SAR, int SAG, int a_stage, int n_work, int n_ntiles, Epi3 ep) {
+           int SB, int TPB, int SAR, int SAG, int a_stage, int GRP, int n_work, int n_ntiles, Epi3 ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_a = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);   // operand-A stages
   uint8_t* smem = smem_a + (SAR + SAG) * a_stage;                                    // everything else (a_stage: A_STAGE, or PLAIN_BYTES for plain-tile launches)
@@ -224,6 +233,35 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     KEnt3 en_next = tab[0];           // the table is read one entry ahead: an ld.shared takes ~200 clk here
     for (int w = cid; w < n_work; w += ncl) {
       const Tile t = decode_tile(w, n_ntiles, rank, g, BN);
+      if (GRP > 1) {
+        // plain tiles only (no patch, no GroupNorm-folded load): GRP loads per operand stage, their weight tiles in one
+        // weight stage (b_stage = GRP tiles)
+        for (int e = 0; e < nent; e += GRP) {
+          const int ng = nent - e < GRP ? nent - e : GRP;
+          { TRACE_T0(); tc::mbar_wait(&r_empty[ra.i], ra.ph ^ 1); TRACE_ACC(tr_wait); }
+          if (tc::elect_one()) {
+            if (rank == 0) tc::mbar_arrive_expect_tx(&r_full[ra.i], 2u * (uint32_t)ng * PLAIN_BYTES);
+            for (int u = 0; u < ng; ++u) {
+              const KEnt3 en = tab[e + u];
+              const CUtensorMap* ma = en.seg == 0 ? &mapA0 : (en.seg == 1 ? &mapA1 : &mapA2);
+              const int dh = (int)(short)(en.dhw & 0xffff), dw = en.dhw >> 16;
+              tc::tma2_load_4d(smem_a + ra.i * a_stage + u * PLAIN_BYTES, ma, r_full_l + ra.i * 8, en.c0,
+                               t.w0 * en.sc + dw, t.h0 * en.sc + dh, t.n0 + en.dn);
+            }
+          }
+          __syncwarp();
+          ra.next((uint32_t)SAR);
+          { TRACE_T0(); tc::mbar_wait(&b_empty[rb.i], rb.ph ^ 1); TRACE_ACC(tr_wait); }
+          if (tc::elect_one()) {
+            if (rank == 0) tc::mbar_arrive_expect_tx(&b_full[rb.i], 2u * (uint32_t)ng * (uint32_t)b_bytes);
+            for (int u = 0; u < ng; ++u)
+              tc::tma2_load_2d(b_sm + rb.i * b_stage + u * b_bytes, &mapB, b_full_l + rb.i * 8, tab[e + u].kofs, t.nbase + b_row);
+          }
+          __syncwarp();
+          rb.next((uint32_t)SB);
+        }
+        continue;
+      }
       for (int e = 0; e < nent; ++e) {
         const KEnt3 en = en_next;
         en_next = tab[e + 1 == nent ? 0 : e + 1];
@@ -284,6 +322,32 @@ k_conv_tc3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * ACC_STRIDE;
         uint32_t acc = 0;
+        if (GRP > 1) {
+          for (int e = 0; e < nent; e += GRP) {
+            const int ng = nent - e < GRP ? nent - e : GRP;
+            { TRACE_T0(); tc::mbar_wait(&r_full[ra.i], ra.ph); TRACE_ACC(tr_ops); TRACE_ACC(tr_a); }
+            { TRACE_T0(); tc::mbar_wait(&b_full[rb.i], rb.ph); TRACE_ACC(tr_ops); }
+            tc::tc_fence_after();
+            const uint64_t adesc = tc::make_sw128_desc(tc::smem_u32(smem_a + ra.i * a_stage));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(rb.i * b_step);
+            if (tc::elect_one()) {
+              for (int u = 0; u < ng; ++u) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  tc::umma2_f16_ss(d_tmem, tc::desc_advance(adesc + (uint64_t)(u * (PLAIN_BYTES >> 4)), k * 32),
+                                   tc::desc_advance(bdesc + (uint64_t)(u * b_tile), k * 32), idesc, (k | u) ? 1u : acc);
+              }
+              tc::umma2_commit_mc(&b_empty[rb.i], 3);
+              tc::umma2_commit_mc(&r_empty[ra.i], 3);
+              if (e + ng >= nent) tc::umma2_commit_mc(&tmem_full[ab], 3);
+            }
+            __syncwarp();
+            acc = 1;
+            rb.next((uint32_t)SB);
+            ra.next((uint32_t)SAR);
+          }
+          continue;
+        }
         for (int e = 0; e < nent; ++e) {
           const int patch = pg_next >> 4;
           const bool gn = (pg_next & 15) != 0;
@@ -947,13 +1011,18 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st, float* out_nch
   bool any_patch = false;
   for (int s = 0; s < p.nseg; ++s) any_patch |= p.seg[s].patch != 0;
   int TPB = (any_patch && BN <= 192) ? 3 : 1;
-  const int b_stage = TPB * b_bytes;
-  int a_stage = A_STAGE;
+  int b_stage = TPB * b_bytes;
+  int a_stage = A_STAGE, GRP = 1;
   if (EO_CONV_DEEP_RING && !any_patch && !any_gn) {
     // plain tiles only: one weight tile per operand load, so as many (operand, weight) stage pairs as fit
     a_stage = PLAIN_BYTES;
     const int avail = SMEM_LIMIT - 1024 - Smem::VAR_OFF - (has_res ? 2 * STG_BYTES : 0);
-    SAR = std::max(3, std::min(SA_MAX, avail / (a_stage + b_stage)));
+    if (BN <= 192) {        // a 256-wide tile's four MMAs (512 clk) already cover the issue chain
+      for (int cand = std::min(EO_CONV_GROUP_MAX, pl->nkb); cand > 1; --cand)
+        if (EO_CONV_GROUP_STAGES * cand * (PLAIN_BYTES + b_bytes) <= avail) { GRP = cand; break; }
+    }
+    if (GRP > 1) { TPB = GRP; a_stage = GRP * PLAIN_BYTES; b_stage = GRP * b_bytes; }
+    SAR = std::max(GRP > 1 ? 2 : 3, std::min(SA_MAX, avail / (a_stage + b_stage)));
   }
   const int fixed = (SAR + SAG) * a_stage + Smem::VAR_OFF + (has_res ? 2 * STG_BYTES : 0);
   int SB = (SMEM_LIMIT - 1024 - fixed) / b_stage;
@@ -1011,7 +1080,7 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st, float* out_nch
   EO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA[0], pl->mapA[1], pl->mapA[2], pl->mapB, pl->mapOut,
                                    pl->mapRes, (const KEnt3*)pl->d_kblks, pl->nkb,
                                    (const XEnt3*)(reinterpret_cast<const uint8_t*>(pl->d_kblks) + pl->xent_off), pl->n_xent, g, B,
-                                   BN, SB, TPB, SAR, SAG, a_stage, n_work, n_ntiles, ep));
+                                   BN, SB, TPB, SAR, SAG, a_stage, GRP, n_work, n_ntiles, ep));
   return EO_OK;
 }
 
