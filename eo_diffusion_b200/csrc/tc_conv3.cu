@@ -66,6 +66,9 @@ constexpr int SA_MAX = 8;                                  // operand-A stages: 
 #ifndef EO_CONV_GROUP_MAX
 #define EO_CONV_GROUP_MAX 4
 #endif
+#ifndef EO_CONV_GROUP_BNMAX
+#define EO_CONV_GROUP_BNMAX 192      // widest channel tile that is grouped (256: measured neutral to slightly slower)
+#endif
 #ifndef EO_CONV_GROUP_STAGES
 #define EO_CONV_GROUP_STAGES 2       // stage pairs a group size must leave room for
 #endif
@@ -1017,7 +1020,7 @@ int tc_conv3_launch(const TcConvPlan* pl, int B, cudaStream_t st, float* out_nch
     // plain tiles only: one weight tile per operand load, so as many (operand, weight) stage pairs as fit
     a_stage = PLAIN_BYTES;
     const int avail = SMEM_LIMIT - 1024 - Smem::VAR_OFF - (has_res ? 2 * STG_BYTES : 0);
-    if (BN <= 192) {        // a 256-wide tile's four MMAs (512 clk) already cover the issue chain
+    if (BN <= EO_CONV_GROUP_BNMAX) {        // a 256-wide tile's four MMAs (512 clk) already cover the issue chain
       for (int cand = std::min(EO_CONV_GROUP_MAX, pl->nkb); cand > 1; --cand)
         if (EO_CONV_GROUP_STAGES * cand * (PLAIN_BYTES + b_bytes) <= avail) { GRP = cand; break; }
     }
