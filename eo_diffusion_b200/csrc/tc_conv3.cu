@@ -20,6 +20,11 @@
 //     swizzle is a function of the absolute address, tools/probe_shifted_desc.cu), cutting the
 //     activation traffic L2 -> SM from 9 x 16 KB to 22.5 KB per 64 channels.
 //
+//   * launches made of plain 128-pixel tiles only (1x1 and stride-2 convolutions, 3x3 windows over maps that take no
+//     halo patch) feed four MMAs per operand load, fewer clocks of tensor-pipe work than the MMA warp's wait / fence /
+//     issue / commit chain: they pack 16 KB operand stages and hand the MMA warp groups of up to four K blocks per
+//     barrier round trip (GRP; EO_CONV_GROUP_MAX below).
+//
 //   * GroupNorm + SiLU of the operand folded in: for such a segment the halo patch is not fetched by
 //     TMA; four transform warps load it from global memory into registers, apply
 //     act(x * scale[n,c] + shift[n,c]) and write the 128B-swizzled operand stage themselves (zeros for
