@@ -264,7 +264,7 @@ def main():
     nparam = sum(p.numel() for p in m_base.parameters())
     assert nparam == 88220934, nparam  # EO_Diffusion.ipynb:151
     manifest["param_count_base"] = nparam
-    for tval in (500, 1, 0):
+    for tval in (750, 500, 250, 1, 0):    # with 999 above: the timesteps SURVEY.md 8(d) lists
         g = torch.Generator().manual_seed(100 + tval)
         x = torch.randn((1, 3, 64, 64), generator=g)
         t = torch.tensor([tval])

@@ -38,8 +38,8 @@ def model_for(g, dev, mode):
 
 
 @pytest.mark.parametrize("name", ["tiny_eps", "tiny_eps_b3", "tiny_concat_eps", "small_eps",
-                                  "small_ms_concat_eps", "base64_eps", "base64_eps_t500",
-                                  "base64_eps_t1", "base64_eps_t0",
+                                  "small_ms_concat_eps", "base64_eps", "base64_eps_t750", "base64_eps_t500",
+                                  "base64_eps_t250", "base64_eps_t1", "base64_eps_t0",   # t in {999, 750, 500, 250, 1, 0}
                                   # FiLM conditioning / up-down ResBlocks (the reference's UNet* factories)
                                   "tiny_film_eps", "tiny_updown_eps", "tiny_film_updown_eps", "small_film_updown_eps"])
 def test_eps_fp32_mode(cuda_dev, name):
@@ -53,8 +53,8 @@ def test_eps_fp32_mode(cuda_dev, name):
     assert err <= TOL["fp32"], f"{name}: rel L2 {err:.3e}"
 
 
-@pytest.mark.parametrize("name", ["small_eps", "small_ms_concat_eps", "base64_eps", "base64_eps_t500",
-                                  "base64_eps_t1", "base64_eps_t0", "small_film_updown_eps"])
+@pytest.mark.parametrize("name", ["small_eps", "small_ms_concat_eps", "base64_eps", "base64_eps_t750", "base64_eps_t500",
+                                  "base64_eps_t250", "base64_eps_t1", "base64_eps_t0", "small_film_updown_eps"])
 def test_eps_bf16_mode(cuda_dev, name):
     g = golden(name)
     m, _ = model_for(g, cuda_dev, "bf16")

@@ -83,7 +83,8 @@ def test_stub_ddim(eta):
 
 
 @pytest.mark.parametrize("name", ["tiny_eps", "tiny_eps_b3", "tiny_concat_eps", "small_eps",
-                                  "small_ms_concat_eps", "base64_eps", "tiny_film_eps", "tiny_updown_eps",
+                                  "small_ms_concat_eps", "base64_eps", "base64_eps_t750", "base64_eps_t250",
+                                  "tiny_film_eps", "tiny_updown_eps",
                                   "tiny_film_updown_eps", "small_film_updown_eps"])
 def test_unet_eps_vs_golden(name):
     g = golden(name)
